@@ -1,0 +1,491 @@
+// smct_capi.cu — extern "C" entry points of libsmct_b200.so (declared in include/smct.h).
+// Host-side argument checking, workspace carving and kernel launches.  No CPU fallback.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <algorithm>
+
+#include "../../include/smct.h"
+#include "smct_common.cuh"
+#include "smct_staged.cuh"
+#include "smct_fused.cuh"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+
+#define SMCT_CUDA(expr)                                                                         \
+  do {                                                                                          \
+    cudaError_t e__ = (expr);                                                                   \
+    if (e__ != cudaSuccess)                                                                     \
+      return fail(SMCT_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+
+#define SMCT_LAUNCH_CHECK(name)                                                                  \
+  do {                                                                                          \
+    cudaError_t e__ = cudaGetLastError();                                                       \
+    if (e__ != cudaSuccess)                                                                     \
+      return fail(SMCT_ERR_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(e__));     \
+  } while (0)
+
+inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+struct Carver {
+  char* base; size_t off, cap;
+  template <typename T> T* take(size_t n) {
+    T* p = (T*)(base + off);
+    off = align_up(off + n * sizeof(T));
+    return p;
+  }
+};
+
+int check_shape(const smct_shape* s) {
+  if (!s) return fail(SMCT_ERR_INVALID, "shape is NULL");
+  if (s->struct_bytes != (int32_t)sizeof(smct_shape))
+    return fail(SMCT_ERR_INVALID, "smct_shape.struct_bytes=%d, library expects %d (ABI %d)", s->struct_bytes,
+                (int)sizeof(smct_shape), SMCT_ABI_VERSION);
+  if (s->B < 1 || s->P < 1 || s->S < 1 || s->D < 1 || s->H < 1 || s->F_y < 1)
+    return fail(SMCT_ERR_INVALID, "B,P,S,D,H,F_y must be >= 1 (got %d,%d,%d,%d,%d,%d)", s->B, s->P, s->S, s->D, s->H, s->F_y);
+  if (s->D % s->H) return fail(SMCT_ERR_INVALID, "d_model %d not divisible by num_heads %d", s->D, s->H);
+  if (s->D > 256) return fail(SMCT_ERR_UNSUPPORTED, "d_model %d > 256 unsupported", s->D);
+  if (s->P > 16384) return fail(SMCT_ERR_UNSUPPORTED, "particles %d > 16384 unsupported", s->P);
+  if (s->full_model && s->dff < 1) return fail(SMCT_ERR_INVALID, "full_model needs dff >= 1");
+  if (s->logvar_dim != 1 && s->logvar_dim != s->D) return fail(SMCT_ERR_INVALID, "logvar_dim must be 1 or D");
+  if (s->weights_mode != SMCT_WEIGHTS_GAUSSIAN && s->weights_mode != SMCT_WEIGHTS_CLASSIFICATION)
+    return fail(SMCT_ERR_INVALID, "bad weights_mode %d", s->weights_mode);
+  if (s->input_mode < 0 || s->input_mode > 2) return fail(SMCT_ERR_INVALID, "bad input_mode %d", s->input_mode);
+  if (s->weights_mode == SMCT_WEIGHTS_GAUSSIAN && !(s->sigma_obs > 0.f))
+    return fail(SMCT_ERR_INVALID, "sigma_obs must be > 0");
+  return SMCT_OK;
+}
+
+size_t step_smem_bytes(int D, int dff, int full_model) {
+  const size_t Dp = D + 1, Fp = dff + 1;
+  return (2 * smct::PT * Dp + (full_model ? smct::PT * Fp : 0) + smct::NW * 3 * (size_t)D + 2 * smct::NW) * sizeof(float);
+}
+
+template <int KD>
+int launch_step_t(const smct::StepArgs& a, cudaStream_t st) {
+  static bool attr_set = false;
+  const size_t smem = step_smem_bytes(a.D, a.dff, a.full_model);
+  if (smem > 200 * 1024) return fail(SMCT_ERR_UNSUPPORTED, "step tile needs %zu B shared memory (D=%d dff=%d)", smem, a.D, a.dff);
+  if (!attr_set) {
+    SMCT_CUDA(cudaFuncSetAttribute(smct::step_kernel<KD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  dim3 grid((a.P + smct::PT - 1) / smct::PT, a.B);
+  smct::step_kernel<KD><<<grid, smct::NT, smem, st>>>(a);
+  SMCT_LAUNCH_CHECK("step_kernel");
+  return SMCT_OK;
+}
+
+int launch_step(const smct::StepArgs& a, cudaStream_t st) {
+  if (a.D <= 32) return launch_step_t<1>(a, st);
+  if (a.D <= 64) return launch_step_t<2>(a, st);
+  if (a.D <= 128) return launch_step_t<4>(a, st);
+  return launch_step_t<8>(a, st);
+}
+
+int launch_rows(const smct::RowsArgs& a, cudaStream_t st) {
+  const size_t smem = (2 * (size_t)a.D + 32) * sizeof(float);
+  const int grid = (int)std::min<long long>(a.rows, 148LL * 16);
+  smct::rows_kernel<<<grid, 128, smem, st>>>(a);
+  SMCT_LAUNCH_CHECK("rows_kernel");
+  return SMCT_OK;
+}
+
+int launch_resample(const smct::ResampleArgs& a, cudaStream_t st) {
+  static bool attr_set = false;
+  const size_t smem = (size_t)a.P * sizeof(double);
+  if (smem > 48 * 1024 && !attr_set) {
+    SMCT_CUDA(cudaFuncSetAttribute(smct::resample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    attr_set = true;
+  }
+  smct::resample_kernel<<<a.B, 256, smem, st>>>(a);
+  SMCT_LAUNCH_CHECK("resample_kernel");
+  return SMCT_OK;
+}
+
+int launch_gather(const smct::GatherArgs& a, int ntensors, cudaStream_t st) {
+  const long long per = ((a.row_elems & 3) == 0 && (a.n_elems & 3) == 0) ? a.n_elems / 4 : a.n_elems;
+  int gy = (int)std::max<long long>(1, std::min<long long>(64, (per + 256 * 8 - 1) / (256 * 8)));
+  dim3 grid((unsigned)((long long)a.B * a.P), gy, ntensors);
+  smct::gather_kernel<<<grid, 256, 0, st>>>(a);
+  SMCT_LAUNCH_CHECK("gather_kernel");
+  return SMCT_OK;
+}
+
+__global__ void fill_f32_kernel(float* p, long long n, float v) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
+}
+
+void fill_step_common(smct::StepArgs& a, const smct_shape& s, const smct_params& pr) {
+  memset(&a, 0, sizeof(a));
+  a.B = s.B; a.P = s.P; a.S = s.S; a.D = s.D; a.H = s.H; a.dff = s.dff; a.Fy = s.F_y;
+  a.full_model = s.full_model; a.weights_mode = s.weights_mode; a.noise_z_mode = s.noise_z_mode;
+  a.noise_on = s.noise_on; a.logvar_dim = s.logvar_dim;
+  a.ln_eps = s.ln_eps; a.sigma_obs = s.sigma_obs;
+  a.b_global0 = s.b_global0;
+  a.p = pr;
+}
+
+// ------------------------------------------------------------------------------------------
+// staged forward: S x (step, resample, gather) with ping-pong state buffers
+// ------------------------------------------------------------------------------------------
+size_t staged_forward_ws(const smct_shape& s) {
+  const size_t rows = (size_t)s.B * std::max(s.S, s.P);
+  size_t n = 0;
+  n += 6 * align_up(rows * s.D * sizeof(float));
+  n += align_up((size_t)s.B * s.P * sizeof(float));
+  n += align_up((size_t)s.B * s.P * sizeof(int));
+  n += 3 * align_up((size_t)s.B * s.P * s.S * s.D * sizeof(float));
+  return n + 1024;
+}
+
+int forward_staged(const smct_shape& s, const smct_params& pr, const smct_io& io, void* ws, size_t ws_bytes,
+                   cudaStream_t st) {
+  if (ws_bytes < staged_forward_ws(s)) return fail(SMCT_ERR_WORKSPACE, "workspace %zu < required %zu", ws_bytes, staged_forward_ws(s));
+  const int B = s.B, P = s.P, S = s.S, D = s.D;
+  const size_t rows = (size_t)B * std::max(S, P);
+  Carver c{(char*)ws, 0, ws_bytes};
+  float* xln = c.take<float>(rows * D);
+  float* q_ = c.take<float>(rows * D);
+  float* k_ = c.take<float>(rows * D);
+  float* v_ = c.take<float>(rows * D);
+  float* kx = c.take<float>(rows * D);
+  float* vx = c.take<float>(rows * D);
+  float* logw = c.take<float>((size_t)B * P);
+  int* idx = c.take<int>((size_t)B * P);
+  const size_t BPSD = (size_t)B * P * S * D;
+  float* K2 = c.take<float>(BPSD);
+  float* V2 = c.take<float>(BPSD);
+  float* R2 = c.take<float>(BPSD);
+
+  if (io.loss_sums) SMCT_CUDA(cudaMemsetAsync(io.loss_sums, 0, 8 * sizeof(double), st));
+  if (io.attn) SMCT_CUDA(cudaMemsetAsync(io.attn, 0, (size_t)B * P * s.H * S * S * sizeof(float), st));
+
+  smct::RowsArgs ra;
+  memset(&ra, 0, sizeof(ra));
+  ra.rows = (long long)B * S; ra.D = D; ra.Fx = s.F_x; ra.input_mode = s.input_mode; ra.do_ln = 1;
+  ra.sqrtD = sqrtf((float)D); ra.ln_eps = s.ln_eps; ra.x_in = io.x_in;
+  ra.W_in = pr.W_in; ra.b_in = pr.b_in; ra.ln_g = pr.ln1_g; ra.ln_b = pr.ln1_b;
+  ra.Wq = pr.Wq; ra.bq = pr.bq; ra.Wk = pr.Wk; ra.bk = pr.bk; ra.Wv = pr.Wv; ra.bv = pr.bv;
+  ra.xln = xln; ra.q_ = q_; ra.k_ = k_; ra.v_ = v_; ra.kx = kx; ra.vx = vx;
+  if (int rc = launch_rows(ra, st)) return rc;
+
+  const int n_gather = s.noise_on ? (s.len_resampling < 0 ? S : std::min(S, std::max(0, s.len_resampling))) : 0;
+  float *Kc, *Vc, *Rc, *Ka, *Va, *Ra;
+  if (n_gather % 2 == 0) { Kc = io.K; Vc = io.V; Rc = io.R; Ka = K2; Va = V2; Ra = R2; }
+  else { Kc = K2; Vc = V2; Rc = R2; Ka = io.K; Va = io.V; Ra = io.R; }
+
+  if (!s.noise_on && io.w) {
+    fill_f32_kernel<<<256, 256, 0, st>>>(io.w, (long long)B * P * S, 1.0f);
+    SMCT_LAUNCH_CHECK("fill_f32_kernel");
+  }
+
+  const size_t BPD = (size_t)B * P * D, BP = (size_t)B * P;
+  for (int t = 0; t < S; ++t) {
+    smct::StepArgs a;
+    fill_step_common(a, s, pr);
+    a.t = t;
+    a.s_lo = (s.attn_window >= 0 && t > s.attn_window) ? t - s.attn_window : 0;
+    a.xln = xln + (size_t)t * D; a.q_ = q_ + (size_t)t * D; a.k_ = k_ + (size_t)t * D; a.v_ = v_ + (size_t)t * D;
+    a.row_sb = (long long)S * D; a.row_sp = 0;
+    if (s.weights_mode == SMCT_WEIGHTS_GAUSSIAN) { a.y = (const float*)io.y + (size_t)t * s.F_y; a.y_sb = (long long)S * s.F_y; }
+    else { a.y = (const int*)io.y + t; a.y_sb = S; }
+    if (io.eps) {
+      a.eps_k = io.eps + ((size_t)0 * S + t) * BPD; a.eps_q = io.eps + ((size_t)1 * S + t) * BPD;
+      a.eps_v = io.eps + ((size_t)2 * S + t) * BPD; a.eps_z = io.eps + ((size_t)3 * S + t) * BPD;
+    }
+    a.seed = io.seed; a.t_rng = t;
+    a.K = Kc; a.V = Vc; a.R = Rc;
+    a.pred = io.pred ? io.pred + (size_t)t * s.F_y : nullptr; a.pred_st = (long long)S * s.F_y;
+    a.noise_q = io.noise_q ? io.noise_q + (size_t)t * D : nullptr;
+    a.noise_z = io.noise_z ? io.noise_z + (size_t)t * D : nullptr;
+    a.nz_st = (long long)S * D;
+    a.attn = io.attn ? io.attn + (size_t)t * S : nullptr;
+    a.attn_st_bp = (long long)s.H * S * S; a.attn_st_h = (long long)S * S;
+    a.logw = logw;
+    a.loss_sums = io.loss_sums;
+    if (int rc = launch_step(a, st)) return rc;
+
+    if (s.noise_on) {
+      smct::ResampleArgs r;
+      memset(&r, 0, sizeof(r));
+      r.B = B; r.P = P; r.normalise = (s.weights_mode == SMCT_WEIGHTS_GAUSSIAN);
+      r.logw = logw;
+      r.u = io.u ? io.u + (size_t)t * BP : nullptr;
+      r.i_forced = io.i_forced ? io.i_forced + (size_t)t * BP : nullptr;
+      r.seed = io.seed; r.b_global0 = s.b_global0; r.t_rng = t;
+      r.w_out = io.w ? io.w + t : nullptr; r.w_st = S;
+      r.logw_copy = io.logw ? io.logw + (size_t)t * BP : nullptr;
+      r.i_out = idx;
+      r.i_out2 = io.i_out ? io.i_out + (size_t)t * BP : nullptr;
+      if (int rc = launch_resample(r, st)) return rc;
+      if (s.len_resampling < 0 || t < s.len_resampling) {
+        smct::GatherArgs g;
+        memset(&g, 0, sizeof(g));
+        g.B = B; g.P = P; g.row_elems = (long long)S * D; g.n_elems = (long long)(t + 1) * D;
+        g.src[0] = Kc; g.src[1] = Vc; g.src[2] = Rc; g.dst[0] = Ka; g.dst[1] = Va; g.dst[2] = Ra; g.idx = idx;
+        if (int rc = launch_gather(g, 3, st)) return rc;
+        std::swap(Kc, Ka); std::swap(Vc, Va); std::swap(Rc, Ra);
+      }
+    }
+  }
+  if (Kc != io.K) return fail(SMCT_ERR_INVALID, "internal: ping-pong parity error");
+
+  smct::FinalArgs f;
+  memset(&f, 0, sizeof(f));
+  f.B = B; f.P = P; f.S = S; f.D = D; f.Fy = s.F_y; f.weights_mode = s.weights_mode; f.logvar_dim = s.logvar_dim;
+  f.K = io.K; f.V = io.V; f.R = io.R;
+  const bool want_noise = io.noise_K || io.noise_V || io.loss_sums;
+  f.kx = want_noise ? kx : nullptr; f.vx = want_noise ? vx : nullptr;
+  f.Wo = pr.Wo; f.logvar_k = pr.logvar_k; f.logvar_v = pr.logvar_v;
+  f.y = (s.weights_mode == SMCT_WEIGHTS_GAUSSIAN) ? io.y : nullptr;
+  f.pred_resampl = io.pred_resampl; f.noise_K = io.noise_K; f.noise_V = io.noise_V; f.loss_sums = io.loss_sums;
+  const long long nrows = (long long)B * P * S;
+  const int grid = (int)std::min<long long>((nrows + 7) / 8, 148LL * 32);
+  smct::final_kernel<<<grid, 256, 0, st>>>(f);
+  SMCT_LAUNCH_CHECK("final_kernel");
+  return SMCT_OK;
+}
+
+}  // namespace
+
+// ==========================================================================================
+// extern "C"
+// ==========================================================================================
+extern "C" {
+
+int smct_abi_version(void) { return SMCT_ABI_VERSION; }
+const char* smct_last_error(void) { return g_last_error.c_str(); }
+const char* smct_build_info(void) {
+#define SMCT_STR2(x) #x
+#define SMCT_STR(x) SMCT_STR2(x)
+  return "libsmct_b200 abi " SMCT_STR(SMCT_ABI_VERSION) " | sm_100a | nvcc " SMCT_STR(__CUDACC_VER_MAJOR__) "." SMCT_STR(
+      __CUDACC_VER_MINOR__) " | " __DATE__ " " __TIME__;
+}
+
+size_t smct_workspace_bytes(const smct_shape* shape) {
+  if (check_shape(shape) != SMCT_OK) return 0;
+  return std::max(staged_forward_ws(*shape), smct::fused_forward_ws(*shape));
+}
+
+int smct_forward(const smct_shape* shape, const smct_params* params, const smct_io* io, void* workspace,
+                 size_t workspace_bytes, void* stream) {
+  if (int rc = check_shape(shape)) return rc;
+  if (!params || !io) return fail(SMCT_ERR_INVALID, "params/io is NULL");
+  if (!io->x_in || !io->K || !io->V || !io->R) return fail(SMCT_ERR_INVALID, "x_in, K, V, R are required");
+  if (shape->noise_on && !io->y) return fail(SMCT_ERR_INVALID, "y (targets) required when noise is on");
+  if (!workspace) return fail(SMCT_ERR_WORKSPACE, "workspace is NULL");
+  cudaStream_t st = (cudaStream_t)stream;
+  int algo = shape->algo;
+  if (algo == SMCT_ALGO_AUTO) algo = smct::fused_supported(*shape, *io) ? SMCT_ALGO_FUSED : SMCT_ALGO_STAGED;
+  if (algo == SMCT_ALGO_FUSED) {
+    if (!smct::fused_supported(*shape, *io)) return fail(SMCT_ERR_UNSUPPORTED, "fused forward does not support this shape/io");
+    const char* err = nullptr;
+    int rc = smct::forward_fused(*shape, *params, *io, workspace, workspace_bytes, st, &err);
+    if (rc) return fail(rc, "%s", err ? err : "fused forward failed");
+    return SMCT_OK;
+  }
+  return forward_staged(*shape, *params, *io, workspace, workspace_bytes, st);
+}
+
+int smct_cell_step(const smct_shape* shape, const smct_params* params, int32_t t, const float* x,
+                   int32_t x_per_particle, const void* y, const float* eps4, const double* u,
+                   const int32_t* i_forced, uint64_t seed, float* K, float* V, float* R, float* r, float* pred,
+                   float* attn, float* noise_q, float* noise_z, float* w, int32_t* i_out, void* workspace,
+                   size_t workspace_bytes, void* stream) {
+  if (int rc = check_shape(shape)) return rc;
+  const smct_shape& s = *shape;
+  if (!params || !x || !K || !V || !R) return fail(SMCT_ERR_INVALID, "params, x, K, V, R are required");
+  if (t < 0 || t >= s.S) return fail(SMCT_ERR_INVALID, "timestep %d outside [0,%d)", t, s.S);
+  if (s.noise_on && !y) return fail(SMCT_ERR_INVALID, "y required when noise is on");
+  if (!workspace || workspace_bytes < staged_forward_ws(s)) return fail(SMCT_ERR_WORKSPACE, "workspace %zu < required %zu", workspace_bytes, staged_forward_ws(s));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int B = s.B, P = s.P, S = s.S, D = s.D;
+  const size_t rows_cap = (size_t)B * std::max(S, P);
+  Carver c{(char*)workspace, 0, workspace_bytes};
+  float* xln = c.take<float>(rows_cap * D);
+  float* q_ = c.take<float>(rows_cap * D);
+  float* k_ = c.take<float>(rows_cap * D);
+  float* v_ = c.take<float>(rows_cap * D);
+  c.take<float>(rows_cap * D); c.take<float>(rows_cap * D);
+  float* logw = c.take<float>((size_t)B * P);
+  int* idx = c.take<int>((size_t)B * P);
+  const size_t BPSD = (size_t)B * P * S * D;
+  float* K2 = c.take<float>(BPSD);
+  float* V2 = c.take<float>(BPSD);
+  float* R2 = c.take<float>(BPSD);
+
+  smct::RowsArgs ra;
+  memset(&ra, 0, sizeof(ra));
+  ra.rows = x_per_particle ? (long long)B * P : B; ra.D = D; ra.Fx = s.F_x; ra.input_mode = SMCT_INPUT_ENCODED; ra.do_ln = 1;
+  ra.sqrtD = 1.f; ra.ln_eps = s.ln_eps; ra.x_in = x;
+  ra.ln_g = params->ln1_g; ra.ln_b = params->ln1_b;
+  ra.Wq = params->Wq; ra.bq = params->bq; ra.Wk = params->Wk; ra.bk = params->bk; ra.Wv = params->Wv; ra.bv = params->bv;
+  ra.xln = xln; ra.q_ = q_; ra.k_ = k_; ra.v_ = v_;
+  if (int rc = launch_rows(ra, st)) return rc;
+  if (attn) SMCT_CUDA(cudaMemsetAsync(attn, 0, (size_t)B * P * s.H * S * sizeof(float), st));
+
+  smct::StepArgs a;
+  fill_step_common(a, s, *params);
+  a.t = t; a.s_lo = (s.attn_window >= 0 && t > s.attn_window) ? t - s.attn_window : 0;
+  a.xln = xln; a.q_ = q_; a.k_ = k_; a.v_ = v_;
+  a.row_sb = x_per_particle ? (long long)P * D : D; a.row_sp = x_per_particle ? D : 0;
+  a.y = y; a.y_sb = (s.weights_mode == SMCT_WEIGHTS_GAUSSIAN) ? s.F_y : 1;
+  const size_t BPD = (size_t)B * P * D;
+  if (eps4) { a.eps_k = eps4; a.eps_q = eps4 + BPD; a.eps_v = eps4 + 2 * BPD; a.eps_z = eps4 + 3 * BPD; }
+  a.seed = seed; a.t_rng = t;
+  a.K = K; a.V = V; a.R = R;
+  a.pred = pred; a.pred_st = s.F_y;
+  a.r_out = r; a.r_st = D;
+  a.noise_q = noise_q; a.noise_z = noise_z; a.nz_st = D;
+  a.attn = attn; a.attn_st_bp = (long long)s.H * S; a.attn_st_h = S;
+  a.logw = logw;
+  if (int rc = launch_step(a, st)) return rc;
+  if (s.noise_on) {
+    smct::ResampleArgs rs;
+    memset(&rs, 0, sizeof(rs));
+    rs.B = B; rs.P = P; rs.normalise = (s.weights_mode == SMCT_WEIGHTS_GAUSSIAN);
+    rs.logw = logw; rs.u = u; rs.i_forced = i_forced; rs.seed = seed; rs.b_global0 = s.b_global0; rs.t_rng = t;
+    rs.w_out = w; rs.w_st = 1; rs.i_out = idx; rs.i_out2 = i_out;
+    if (int rc = launch_resample(rs, st)) return rc;
+    if (s.len_resampling < 0 || t < s.len_resampling) {
+      // the reference gathers whole rows (all S slots): tf.gather on (B,P,S,3D), SMC_TransformerCell.py:170-172
+      smct::GatherArgs g;
+      memset(&g, 0, sizeof(g));
+      g.B = B; g.P = P; g.row_elems = (long long)S * D; g.n_elems = (long long)S * D;
+      g.src[0] = K; g.src[1] = V; g.src[2] = R; g.dst[0] = K2; g.dst[1] = V2; g.dst[2] = R2; g.idx = idx;
+      if (int rc = launch_gather(g, 3, st)) return rc;
+      SMCT_CUDA(cudaMemcpyAsync(K, K2, BPSD * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      SMCT_CUDA(cudaMemcpyAsync(V, V2, BPSD * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      SMCT_CUDA(cudaMemcpyAsync(R, R2, BPSD * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    }
+  } else if (w) {
+    fill_f32_kernel<<<64, 256, 0, st>>>(w, (long long)B * P, 1.0f);
+    SMCT_LAUNCH_CHECK("fill_f32_kernel");
+  }
+  return SMCT_OK;
+}
+
+int smct_attention_step(const smct_shape* shape, const smct_params* params, int32_t t, const float* inputs,
+                        const float* eps4, uint64_t seed, float* K, float* V, float* z, float* attn,
+                        float* noise_k, float* noise_q, float* noise_v, float* noise_z, void* workspace,
+                        size_t workspace_bytes, void* stream) {
+  if (int rc = check_shape(shape)) return rc;
+  const smct_shape& s = *shape;
+  if (!params || !inputs || !K || !V || !z) return fail(SMCT_ERR_INVALID, "params, inputs, K, V, z are required");
+  if (t < 0 || t >= s.S) return fail(SMCT_ERR_INVALID, "timestep %d outside [0,%d)", t, s.S);
+  if (!workspace || workspace_bytes < staged_forward_ws(s)) return fail(SMCT_ERR_WORKSPACE, "workspace %zu < required %zu", workspace_bytes, staged_forward_ws(s));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int B = s.B, P = s.P, S = s.S, D = s.D;
+  const size_t rows_cap = (size_t)B * std::max(S, P);
+  Carver c{(char*)workspace, 0, workspace_bytes};
+  c.take<float>(rows_cap * D);
+  float* q_ = c.take<float>(rows_cap * D);
+  float* k_ = c.take<float>(rows_cap * D);
+  float* v_ = c.take<float>(rows_cap * D);
+
+  smct::RowsArgs ra;
+  memset(&ra, 0, sizeof(ra));
+  ra.rows = (long long)B * P; ra.D = D; ra.Fx = s.F_x; ra.input_mode = SMCT_INPUT_ENCODED; ra.do_ln = 0;
+  ra.sqrtD = 1.f; ra.ln_eps = s.ln_eps; ra.x_in = inputs;
+  ra.Wq = params->Wq; ra.bq = params->bq; ra.Wk = params->Wk; ra.bk = params->bk; ra.Wv = params->Wv; ra.bv = params->bv;
+  ra.q_ = q_; ra.k_ = k_; ra.v_ = v_;
+  if (int rc = launch_rows(ra, st)) return rc;
+  if (attn) SMCT_CUDA(cudaMemsetAsync(attn, 0, (size_t)B * P * s.H * S * sizeof(float), st));
+
+  smct::StepArgs a;
+  fill_step_common(a, s, *params);
+  a.full_model = 0; a.attn_only = 1;
+  a.t = t; a.s_lo = (s.attn_window >= 0 && t > s.attn_window) ? t - s.attn_window : 0;
+  a.xln = inputs; a.q_ = q_; a.k_ = k_; a.v_ = v_;
+  a.row_sb = (long long)P * D; a.row_sp = D;
+  const size_t BPD = (size_t)B * P * D;
+  if (eps4) { a.eps_k = eps4; a.eps_q = eps4 + BPD; a.eps_v = eps4 + 2 * BPD; a.eps_z = eps4 + 3 * BPD; }
+  a.seed = seed; a.t_rng = t;
+  a.K = K; a.V = V; a.R = nullptr;
+  a.z_out = z; a.z_st = D;
+  a.noise_k = noise_k; a.noise_q = noise_q; a.noise_v = noise_v; a.noise_z = noise_z; a.nz_st = D;
+  a.attn = attn; a.attn_st_bp = (long long)s.H * S; a.attn_st_h = S;
+  return launch_step(a, st);
+}
+
+int smct_logweights(int32_t B, int32_t P, int32_t F_y, int32_t weights_mode, float sigma_obs, const float* pred,
+                    const void* y, float* logw, void* stream) {
+  if (B < 1 || P < 1 || F_y < 1 || !pred || !y || !logw) return fail(SMCT_ERR_INVALID, "smct_logweights: bad arguments");
+  if (weights_mode == SMCT_WEIGHTS_GAUSSIAN && !(sigma_obs > 0.f)) return fail(SMCT_ERR_INVALID, "sigma_obs must be > 0");
+  const long long n = (long long)B * P;
+  smct::logweights_kernel<<<(int)std::min<long long>((n + 255) / 256, 148 * 8), 256, 0, (cudaStream_t)stream>>>(
+      B, P, F_y, weights_mode, sigma_obs, pred, y, logw);
+  SMCT_LAUNCH_CHECK("logweights_kernel");
+  return SMCT_OK;
+}
+
+int smct_resample(int32_t B, int32_t P, int32_t normalise, const float* logw, const double* u, float* w_out,
+                  float* logits_out, int32_t* i_out, void* stream) {
+  if (B < 1 || P < 1 || !logw || !u || !i_out) return fail(SMCT_ERR_INVALID, "smct_resample: bad arguments");
+  if (P > 16384) return fail(SMCT_ERR_UNSUPPORTED, "particles %d > 16384 unsupported", P);
+  smct::ResampleArgs r;
+  memset(&r, 0, sizeof(r));
+  r.B = B; r.P = P; r.normalise = normalise; r.logw = logw; r.u = u;
+  r.w_out = w_out; r.w_st = 1; r.logits_out = logits_out; r.i_out = i_out;
+  return launch_resample(r, (cudaStream_t)stream);
+}
+
+int smct_gather(int32_t B, int32_t P, int64_t row_elems, int64_t n_elems, const float* src, const int32_t* idx,
+                float* dst, void* stream) {
+  if (B < 1 || P < 1 || row_elems < 1 || n_elems < 0 || n_elems > row_elems || !src || !idx || !dst)
+    return fail(SMCT_ERR_INVALID, "smct_gather: bad arguments");
+  if (src == dst) return fail(SMCT_ERR_INVALID, "smct_gather: src and dst must be distinct buffers");
+  if (n_elems == 0) return SMCT_OK;
+  smct::GatherArgs g;
+  memset(&g, 0, sizeof(g));
+  g.B = B; g.P = P; g.row_elems = row_elems; g.n_elems = n_elems; g.src[0] = src; g.dst[0] = dst; g.idx = idx;
+  return launch_gather(g, 1, (cudaStream_t)stream);
+}
+
+int smct_fill_noise(uint64_t seed, int32_t which, int32_t t, int64_t b_global0, int32_t B, int32_t P, int32_t D,
+                    float* out, void* stream) {
+  if (which < 0 || which > 3 || B < 1 || P < 1 || D < 1 || !out) return fail(SMCT_ERR_INVALID, "smct_fill_noise: bad arguments");
+  const long long n = (long long)B * P * ((D + 3) / 4);
+  smct::fill_noise_kernel<<<(int)std::min<long long>((n + 255) / 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(
+      seed, which, t, b_global0, B, P, D, out);
+  SMCT_LAUNCH_CHECK("fill_noise_kernel");
+  return SMCT_OK;
+}
+
+int smct_fill_uniform(uint64_t seed, int32_t t, int64_t b_global0, int32_t B, int32_t P, double* out, void* stream) {
+  if (B < 1 || P < 1 || !out) return fail(SMCT_ERR_INVALID, "smct_fill_uniform: bad arguments");
+  const long long n = (long long)B * P;
+  smct::fill_uniform_kernel<<<(int)std::min<long long>((n + 255) / 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(
+      seed, t, b_global0, B, P, out);
+  SMCT_LAUNCH_CHECK("fill_uniform_kernel");
+  return SMCT_OK;
+}
+
+int smct_sumsq_scaled(int64_t rows, int32_t D, const float* n, const float* logvar, int32_t logvar_dim, double* out,
+                      void* stream) {
+  if (rows < 1 || D < 1 || !n || !logvar || !out || (logvar_dim != 1 && logvar_dim != D))
+    return fail(SMCT_ERR_INVALID, "smct_sumsq_scaled: bad arguments");
+  const long long total = rows * D;
+  smct::sumsq_scaled_kernel<<<(int)std::min<long long>((total + 255) / 256, 148 * 8), 256, 0, (cudaStream_t)stream>>>(
+      rows, D, n, logvar, logvar_dim, out);
+  SMCT_LAUNCH_CHECK("sumsq_scaled_kernel");
+  return SMCT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,105 @@
+// smct_common.cuh — shared device helpers: warp/block reductions, Philox4x32-10 + Box-Muller,
+// LayerNorm (Keras non-fused form).  sm_100a only.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+#define SMCT_FULL_MASK 0xffffffffu
+
+namespace smct {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(SMCT_FULL_MASK, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(SMCT_FULL_MASK, v, o));
+  return v;
+}
+// reduction over aligned groups of G lanes (G power of two <= 32)
+template <int G>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(SMCT_FULL_MASK, v, o);
+  return v;
+}
+
+// block-wide reductions through a 32-float scratch (all threads get the result)
+__device__ __forceinline__ float block_sum(float v, float* scratch) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) scratch[wid] = v;
+  __syncthreads();
+  float r = (lane < nw) ? scratch[lane] : 0.f;
+  return warp_sum(r);
+}
+__device__ __forceinline__ float block_max(float v, float* scratch) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_max(v);
+  __syncthreads();
+  if (lane == 0) scratch[wid] = v;
+  __syncthreads();
+  float r = (lane < nw) ? scratch[lane] : -INFINITY;
+  return warp_max(r);
+}
+
+// ------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al. SC'11).  Stream layout documented in oracle/philox.py:
+//   key = (seed_lo, seed_hi); counter = (group_lo, group_hi, stream, t)
+// ------------------------------------------------------------------------------------------
+struct u32x4 { uint32_t x, y, z, w; };
+
+__device__ __forceinline__ u32x4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                               uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  return u32x4{c0, c1, c2, c3};
+}
+
+__device__ __forceinline__ float u01_f32(uint32_t x) {
+  return (float)(x >> 9) * 1.1920928955078125e-07f + 5.9604644775390625e-08f;  // 2^-23, 2^-24
+}
+
+__device__ __forceinline__ void box_muller(uint32_t xa, uint32_t xb, float& n0, float& n1) {
+  const float u1 = u01_f32(xa), u2 = u01_f32(xb);
+  const float r = sqrtf(-2.0f * __logf(u1));
+  float s, c;
+  __sincosf(6.283185307179586f * (u2 - 0.5f), &s, &c);
+  n0 = r * c; n1 = r * s;
+}
+
+// four standard normals of group `grp` (64-bit) in stream `which` at timestep t
+__device__ __forceinline__ void philox_normal4(uint64_t seed, uint32_t which, uint32_t t, uint64_t grp,
+                                               float n[4]) {
+  const u32x4 x = philox4x32_10((uint32_t)grp, (uint32_t)(grp >> 32), which, t, (uint32_t)seed,
+                                (uint32_t)(seed >> 32));
+  box_muller(x.x, x.y, n[0], n[1]);
+  box_muller(x.z, x.w, n[2], n[3]);
+}
+
+// one standard normal: element d of particle bp (global particle index) with GD = ceil(D/4)
+__device__ __forceinline__ float philox_normal1(uint64_t seed, uint32_t which, uint32_t t, uint64_t bp,
+                                                int GD, int d) {
+  float n[4];
+  philox_normal4(seed, which, t, bp * (uint64_t)GD + (uint64_t)(d >> 2), n);
+  const int e = d & 3;
+  return e == 0 ? n[0] : (e == 1 ? n[1] : (e == 2 ? n[2] : n[3]));
+}
+
+__device__ __forceinline__ double philox_uniform(uint64_t seed, uint32_t t, uint64_t bp) {
+  const u32x4 x = philox4x32_10((uint32_t)bp, (uint32_t)(bp >> 32), 4u, t, (uint32_t)seed,
+                                (uint32_t)(seed >> 32));
+  return ((double)(x.x >> 5) * 67108864.0 + (double)(x.y >> 6)) * 1.1102230246251565e-16;  // 2^-53
+}
+
+}  // namespace smct

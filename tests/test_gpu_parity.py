@@ -1,0 +1,276 @@
+"""GPU parity tests: the CUDA path (through the C-ABI) against the CPU oracle on the same seeded inputs.
+Protocol levels: L0 resampler bit-exact, L1 gather bit-exact, L2 per-stage 1e-4,
+L3 teacher-forced forward, L4 free-running forward with margin-screened uniforms."""
+import numpy as np
+import pytest
+import torch
+
+import smct_b200.functional as F
+from oracle import philox as PH
+from oracle import smct_oracle as O
+from tests import util
+from tests.cases import BIG_CASES, CASES
+
+pytestmark = pytest.mark.gpu
+
+
+# ----------------------------------------------------------------------------- L0 resampler
+@pytest.mark.parametrize("B,P", [(1, 1), (3, 7), (32, 10), (8, 100), (4, 1000), (4, 1024), (2, 4097)])
+def test_resample_bitexact_raw_logits(B, P):
+    rng = np.random.default_rng(B * 1000 + P)
+    logits = (3.0 * rng.standard_normal((B, P))).astype(np.float32)
+    u = rng.random((B, P))
+    u[0, 0] = 0.0
+    u[-1, -1] = np.nextafter(1.0, 0.0)
+    ref = O.categorical_tf_cpu(logits, u)
+    i_t, w, lg = F.resample_indices(torch.as_tensor(logits, device="cuda"), torch.as_tensor(u, device="cuda"), normalise=False)
+    assert np.array_equal(i_t.cpu().numpy().astype(np.int64), ref)
+    assert np.array_equal(w.cpu().numpy(), logits) and np.array_equal(lg.cpu().numpy(), logits)
+
+
+def test_resample_degenerate_weights():
+    # one dominant particle, -inf entries, ties
+    B, P = 4, 64
+    logits = np.full((B, P), -50.0, np.float32)
+    logits[0, 5] = 0.0
+    logits[1, :] = 0.0
+    logits[2, ::2] = -np.inf
+    logits[3, -1] = 10.0
+    u = np.random.default_rng(0).random((B, P))
+    ref = O.categorical_tf_cpu(logits, u)
+    i_t, _, _ = F.resample_indices(torch.as_tensor(logits, device="cuda"), torch.as_tensor(u, device="cuda"), normalise=False)
+    got = i_t.cpu().numpy()
+    assert np.array_equal(got.astype(np.int64), ref)
+    assert (got[0] == 5).all() and (got[3] == P - 1).all() and (got[2] % 2 == 1).all()
+
+
+@pytest.mark.parametrize("B,P", [(6, 10), (3, 1024)])
+def test_resample_normalised_gaussian(B, P):
+    rng = np.random.default_rng(P)
+    logw = (-0.5 * rng.standard_normal((B, P)) ** 2 / 0.5).astype(np.float32)
+    u = rng.random((B, P))
+    i_t, w, lg = F.resample_indices(torch.as_tensor(logw, device="cuda"), torch.as_tensor(u, device="cuda"), normalise=True)
+    lg = lg.cpu().numpy()
+    m = logw.max(1, keepdims=True)
+    ref_lg = logw - (m + np.log(np.exp(logw - m).sum(1, keepdims=True)))
+    util.assert_close("logits", lg, ref_lg)
+    util.assert_close("w", w.cpu().numpy(), np.exp(ref_lg))
+    # bit-exact given the device's own fp32 logits
+    assert np.array_equal(i_t.cpu().numpy().astype(np.int64), O.categorical_tf_cpu(lg, u))
+
+
+# ----------------------------------------------------------------------------- L1 gather
+def test_gather_reference_kat():
+    """transformer_utils.py:66-88 tables (rows <= t gathered, rows > t kept)."""
+    B, S, P = 2, 3, 4
+    ind = np.array([[[1, 1, 2, 2], [0, 0, 0, 0], [1, 1, 1, 0]], [[0, 1, 3, 2], [3, 3, 2, 0], [1, 2, 3, 1]]]).transpose(0, 2, 1)
+    K = np.array([[[1, 2, 3, 4], [5, 6, 7, 8], [9, 10, 11, 12]],
+                  [[13, 14, 15, 16], [17, 18, 19, 20], [21, 22, 23, 24]]]).transpose(0, 2, 1)[..., None].astype(np.float32)
+    truth = {0: [[[2, 5, 9], [2, 6, 10], [3, 7, 11], [3, 8, 12]], [[13, 17, 21], [14, 18, 22], [16, 19, 23], [15, 20, 24]]],
+             1: [[[2, 5, 9], [2, 5, 10], [2, 5, 11], [2, 5, 12]], [[15, 20, 21], [15, 20, 22], [16, 19, 23], [13, 17, 24]]],
+             2: [[[2, 5, 10], [2, 5, 10], [2, 5, 10], [2, 5, 9]], [[15, 20, 22], [16, 19, 23], [13, 17, 24], [15, 20, 22]]]}
+    cur = torch.as_tensor(K, device="cuda").contiguous()
+    for t in range(S):
+        i_t = torch.as_tensor(np.ascontiguousarray(ind[:, :, t]).astype(np.int32), device="cuda")
+        cur = F.gather(cur, i_t, n_elems=(t + 1) * 1)
+        assert np.array_equal(cur.cpu().numpy()[..., 0], np.array(truth[t], np.float32)), t
+
+
+@pytest.mark.parametrize("B,P,S,D", [(2, 5, 3, 1), (3, 33, 7, 6), (2, 100, 24, 8), (2, 64, 16, 64)])
+def test_gather_bitexact(B, P, S, D):
+    rng = np.random.default_rng(D)
+    x = rng.standard_normal((B, P, S, 3 * D)).astype(np.float32)
+    i_t = rng.integers(0, P, size=(B, P)).astype(np.int32)
+    got = F.gather(torch.as_tensor(x, device="cuda"), torch.as_tensor(i_t, device="cuda")).cpu().numpy()
+    assert np.array_equal(got, O.resample(x, i_t))
+    xs = np.ascontiguousarray(x[..., :D])
+    for t in (0, S // 2, S - 1):
+        got = F.gather(torch.as_tensor(xs, device="cuda"), torch.as_tensor(i_t, device="cuda"), n_elems=(t + 1) * D).cpu().numpy()
+        assert np.array_equal(got, O.resample_rows_le_t(xs, i_t, t))
+
+
+# ----------------------------------------------------------------------------- RNG
+def test_philox_streams_match_host_restatement():
+    seed, b0, B, P, D = 0x1234ABCD5678, 3, 5, 37, 10
+    for which in range(4):
+        got = F.fill_noise(seed, which, 7, b0, B, P, D).cpu().numpy()
+        ref = PH.normals(seed, which, 7, b0, B, P, D)
+        assert np.abs(got - ref).max() < 2e-5
+    got_u = F.fill_uniform(seed, 11, b0, B, P).cpu().numpy()
+    assert np.array_equal(got_u, PH.uniforms(seed, 11, b0, B, P))  # integer -> fp64: exact
+    big = F.fill_noise(1, 0, 0, 0, 64, 128, 64).cpu().numpy().astype(np.float64)
+    assert abs(big.mean()) < 5e-3 and abs(big.std() - 1) < 5e-3 and abs((big ** 4).mean() - 3) < 0.05
+
+
+# ----------------------------------------------------------------------------- L2 stages
+def test_logweights_stage():
+    rng = np.random.default_rng(3)
+    pred = rng.standard_normal((6, 20, 5)).astype(np.float32)
+    y = rng.standard_normal((6, 5)).astype(np.float32)
+    got = F.logweights(torch.as_tensor(pred, device="cuda"), torch.as_tensor(y, device="cuda"), "gaussian", 0.5).cpu().numpy()
+    util.assert_close("logw", got, O.compute_w_regression(pred, y, 0.5)[0])
+    ytok = rng.integers(0, 5, size=(6,)).astype(np.int32)
+    got = F.logweights(torch.as_tensor(pred, device="cuda"), torch.as_tensor(ytok, device="cuda"), "classification").cpu().numpy()
+    util.assert_close("w_cls", got, O.compute_w_classification(pred, ytok))
+
+
+def test_squared_norm_kat():
+    """SMC_Transformer.py:361-365: einsum('bijk,bijk->bij') of [[.1,1],...,[.5,5]] == [1.01,4.04,9.09,16.16,25.25]."""
+    x = torch.tensor([[.1, 1], [.2, 2], [.3, 3], [.4, 4], [.5, 5]], dtype=torch.float32, device="cuda")
+    for i, ref in enumerate([1.01, 4.04, 9.09, 16.16, 25.25]):
+        got = F.sumsq_scaled(x[i:i + 1].contiguous(), torch.zeros(1, device="cuda")).item()
+        assert abs(got - ref) < 1e-5
+
+
+@pytest.mark.parametrize("name", ["heads3", "window2", "d64"])
+def test_attention_layer_stage(name):
+    """Self_Attention_SMC.call with per-particle inputs and a random (non-zero) K/V history."""
+    cfg = CASES[name]["cfg"]
+    p = O.init_params(cfg, sigma2=CASES[name]["sigma2"], random_bias=True)
+    rng = np.random.default_rng(11)
+    B, P, S, D = cfg.B, cfg.P, cfg.S, cfg.D
+    t = S - 2
+    x = rng.standard_normal((B, P, D)).astype(np.float32)
+    K = rng.standard_normal((B, P, S, D)).astype(np.float32)
+    V = rng.standard_normal((B, P, S, D)).astype(np.float32)
+    eps4 = rng.standard_normal((4, B, P, D)).astype(np.float32)
+    # oracle, following self_attention_SMC.py:140-193
+    k_, q_, v_ = (O.dense(x, p["W" + n], p["b" + n]) for n in ("k", "q", "v"))
+    k = k_ + O.noise_std(p["logvar_k"]) * eps4[0]
+    q = q_ + O.noise_std(p["logvar_q"]) * eps4[1]
+    v = v_ + O.noise_std(p["logvar_v"]) * eps4[2]
+    K2, V2 = K.copy(), V.copy()
+    K2[:, :, t], V2[:, :, t] = k, v
+    z_, att = O.attention_step(cfg, q.astype(np.float32), K2, V2, t)
+    z = O.dense(z_, p["Wz"], p["bz"]) + O.noise_std(p["logvar_z"]) * eps4[3]
+    shape = F.shape_from_config(cfg, logvar_dim=util.logvar_dim(p))
+    Kd, Vd = torch.as_tensor(K, device="cuda"), torch.as_tensor(V, device="cuda")
+    out = F.attention_step(shape, util.dev_params(p), t, torch.as_tensor(x, device="cuda"), Kd, Vd,
+                           torch.as_tensor(eps4, device="cuda"))
+    util.assert_close("z", out["z"].cpu().numpy(), z)
+    util.assert_close("attn", out["attn"].cpu().numpy(), att)
+    util.assert_close("K", Kd.cpu().numpy(), K2)
+    util.assert_close("V", Vd.cpu().numpy(), V2)
+    util.assert_close("noise_q", out["noise_q"].cpu().numpy(), q - q_)
+    util.assert_close("noise_z", out["noise_z"].cpu().numpy(), z - z_)
+
+
+def test_cell_step_matches_forward_trace():
+    """SMC_Transf_Cell.call on explicit states, driven step by step, reproduces the oracle trajectory."""
+    name = "c3_b8"
+    cfg = CASES[name]["cfg"]
+    p, x_in, y, eps, u = util.make_case(cfg, sigma2=CASES[name]["sigma2"])
+    ora = O.forward(cfg, p, x_in, y, eps, u, trace=True)
+    shape = F.shape_from_config(cfg, logvar_dim=util.logvar_dim(p))
+    dp = util.dev_params(p)
+    B, P, S, D = cfg.B, cfg.P, cfg.S, cfg.D
+    K = torch.zeros((B, P, S, D), device="cuda")
+    V = torch.zeros_like(K)
+    R = torch.zeros_like(K)
+    X = torch.as_tensor(ora["X"], device="cuda")
+    for t in range(S):
+        st = F.cell_step(shape, dp, t, X[:, t].contiguous(), torch.as_tensor(y[:, t], device="cuda").contiguous(), K, V, R,
+                         eps4=torch.as_tensor(eps[:, t], device="cuda").contiguous(),
+                         i_forced=torch.as_tensor(ora["i_t"][t].astype(np.int32), device="cuda"))
+        util.assert_close("r[%d]" % t, st["r"].cpu().numpy(), ora["steps"][t]["r"])
+        util.assert_close("pred[%d]" % t, st["pred"].cpu().numpy(), ora["steps"][t]["pred"])
+        util.assert_close("w[%d]" % t, st["w"].cpu().numpy(), ora["w"][:, :, t])
+    util.assert_close("K", K.cpu().numpy(), ora["K"])
+    util.assert_close("R", R.cpu().numpy(), ora["R"])
+
+
+# ----------------------------------------------------------------------------- L3 / L4 forward
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_forward_teacher_forced(name):
+    c = CASES[name]
+    cfg = c["cfg"]
+    p, x_in, y, eps, u = util.make_case(cfg, sigma2=c["sigma2"], multi=c.get("multi", False))
+    ora = O.forward(cfg, p, x_in, y, eps, u)
+    dev = util.run_device(cfg, p, x_in, y, eps, u, i_forced=ora["i_t"] if cfg.noise else None)
+    util.compare_forward(cfg, p, dev, ora, y)
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_forward_free_running(name):
+    c = CASES[name]
+    cfg = c["cfg"]
+    p, x_in, y, eps, u = util.make_case(cfg, seed=1, sigma2=c["sigma2"], multi=c.get("multi", False))
+    if cfg.noise:
+        u, ora = util.screen_uniforms(cfg, p, x_in, y, eps, u)
+    else:
+        ora = O.forward(cfg, p, x_in, y, eps, u)
+    dev = util.run_device(cfg, p, x_in, y, eps, u)
+    util.compare_forward(cfg, p, dev, ora, y, check_indices=True)
+
+
+@pytest.mark.parametrize("name", sorted(BIG_CASES))
+def test_forward_c4_particle_count(name):
+    c = BIG_CASES[name]
+    cfg = c["cfg"]
+    p, x_in, y, eps, u = util.make_case(cfg, sigma2=c["sigma2"])
+    u, ora = util.screen_uniforms(cfg, p, x_in, y, eps, u)
+    dev = util.run_device(cfg, p, x_in, y, eps, u, want=("i_out", "logw", "loss_sums"))
+    util.compare_forward(cfg, p, dev, ora, y)
+
+
+def test_forward_device_rng_matches_oracle_with_same_draws():
+    """Throughput mode (Philox on device): read the very same draws back through smct_fill_* and
+    inject them into the oracle."""
+    cfg = CASES["c3_b8"]["cfg"]
+    p, x_in, y, _, _ = util.make_case(cfg, sigma2=0.5)
+    seed, b0 = 20261019, 40
+    eps = np.stack([np.stack([F.fill_noise(seed, w, t, b0, cfg.B, cfg.P, cfg.D).cpu().numpy() for t in range(cfg.S)])
+                    for w in range(4)])
+    u = np.stack([F.fill_uniform(seed, t, b0, cfg.B, cfg.P).cpu().numpy() for t in range(cfg.S)])
+    dev = util.run_device(cfg, p, x_in, y, None, None, seed=seed, b_global0=b0)
+    ora = O.forward(cfg, p, x_in, y, eps, u, i_forced=dev["i_out"])
+    util.compare_forward(cfg, p, dev, ora, y)
+    free = O.forward(cfg, p, x_in, y, eps, u)
+    margins = np.array([O.cdf_margin(free["logits"][t], u[t]).min() for t in range(cfg.S)])
+    if margins.min() > 1e-6:
+        assert np.array_equal(dev["i_out"].astype(np.int64), free["i_t"])
+
+
+def test_golden_fixtures():
+    """The committed fixtures (tests/golden/*.npz, written by oracle/gen_golden.py) against the CUDA path."""
+    import glob
+    import os
+    files = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "oracle_*.npz")))
+    assert files, "no golden fixtures"
+    for f in files:
+        g = np.load(f, allow_pickle=True)
+        name = str(g["case"])
+        c = CASES[name]
+        cfg = c["cfg"]
+        p = {k[2:]: g[k] for k in g.files if k.startswith("p_")}
+        dev = util.run_device(cfg, p, g["x_in"], g["y"], g["eps"], g["u"], want=("i_out", "logw"))
+        assert np.array_equal(dev["i_out"].astype(np.int64), g["i_t"]), f
+        for k in ("pred", "pred_resampl", "w"):
+            util.assert_close(name + ":" + k, dev[k], g[k])
+        util.assert_close(name + ":K_last", dev["K"][:, :, -1], g["K_last"])
+        util.assert_close(name + ":R_last", dev["R"][:, :, -1], g["R_last"])
+
+
+# ----------------------------------------------------------------------------- size-independent properties
+def test_properties_at_scale():
+    """Shapes the oracle cannot finish quickly: structural properties of the particle filter."""
+    cfg = O.Config(B=8, P=1024, S=48, D=64, dff=256)
+    p = O.init_params(cfg, sigma2=0.5)
+    x_in, y = O.synthetic_series(cfg.B, cfg.S, 1, alpha=0.9, var=0.3)
+    dev = util.run_device(cfg, p, x_in, y, None, None, seed=7, want=("i_out", "logw", "noise_K", "noise_V"))
+    w = dev["w"].astype(np.float64)
+    assert np.allclose(w.sum(axis=1), 1.0, atol=1e-4)              # normalised weights per (b, t)
+    i = dev["i_out"]
+    assert i.min() >= 0 and i.max() < cfg.P
+    # genealogy: the final state row s of particle m equals slot-s row of its ancestor -> number of
+    # distinct rows at slot s is non-increasing going back in time
+    K = dev["K"]
+    distinct = [len(np.unique(K[0, :, s, 0])) for s in range(cfg.S)]
+    assert all(distinct[s] <= distinct[s + 1] for s in range(cfg.S - 1)), distinct
+    assert distinct[0] < cfg.P // 4
+    # pred_resampl is output_layer(R): linearity check against a host matmul of the returned R
+    ref = dev["R"].astype(np.float64) @ p["Wo"].astype(np.float64)
+    util.assert_close("pred_resampl", dev["pred_resampl"], ref)
+    # re-running with the same seed is bit-identical (no atomics on the data path)
+    dev2 = util.run_device(cfg, p, x_in, y, None, None, seed=7, want=("i_out",))
+    assert np.array_equal(dev2["i_out"], dev["i_out"]) and np.array_equal(dev2["K"], dev["K"])
