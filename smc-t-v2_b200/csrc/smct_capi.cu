@@ -190,9 +190,16 @@ int forward_staged(const smct_shape& s, const smct_params& pr, const smct_io& io
   if (n_gather % 2 == 0) { Kc = io.K; Vc = io.V; Rc = io.R; Ka = K2; Va = V2; Ra = R2; }
   else { Kc = K2; Vc = V2; Rc = R2; Ka = io.K; Va = io.V; Ra = io.R; }
 
-  if (!s.noise_on && io.w) {
-    fill_f32_kernel<<<256, 256, 0, st>>>(io.w, (long long)B * P * S, 1.0f);
-    SMCT_LAUNCH_CHECK("fill_f32_kernel");
+  if (!s.noise_on) {  // SMC_Transformer.py:246: weights are ones, nothing is drawn, no noise is recorded
+    if (io.w) {
+      fill_f32_kernel<<<256, 256, 0, st>>>(io.w, (long long)B * P * S, 1.0f);
+      SMCT_LAUNCH_CHECK("fill_f32_kernel");
+    }
+    const size_t nBPS = (size_t)B * P * S;
+    if (io.i_out) SMCT_CUDA(cudaMemsetAsync(io.i_out, 0, nBPS * sizeof(int), st));
+    if (io.logw) SMCT_CUDA(cudaMemsetAsync(io.logw, 0, nBPS * sizeof(float), st));
+    if (io.noise_q) SMCT_CUDA(cudaMemsetAsync(io.noise_q, 0, nBPS * D * sizeof(float), st));
+    if (io.noise_z) SMCT_CUDA(cudaMemsetAsync(io.noise_z, 0, nBPS * D * sizeof(float), st));
   }
 
   const size_t BPD = (size_t)B * P * D, BP = (size_t)B * P;

@@ -406,7 +406,8 @@ __global__ void __launch_bounds__(NT) step_kernel(const StepArgs a) {
     // output layer (no bias) + weight
     float sq = 0.f, mx = -INFINITY, se = 0.f, py = 0.f;
     int ytok = 0;
-    if (a.weights_mode == SMCT_WEIGHTS_CLASSIFICATION) ytok = ((const int*)a.y)[(long long)b * a.y_sb];
+    const bool do_w = a.logw && a.y;
+    if (do_w && a.weights_mode == SMCT_WEIGHTS_CLASSIFICATION) ytok = ((const int*)a.y)[(long long)b * a.y_sb];
     for (int f = 0; f < a.Fy; ++f) {
       float part = 0.f;
 #pragma unroll
@@ -416,6 +417,7 @@ __global__ void __launch_bounds__(NT) step_kernel(const StepArgs a) {
       }
       const float pr = warp_sum(part);
       if (lane == 0 && a.pred) a.pred[bp * a.pred_st + f] = pr;
+      if (!do_w) continue;
       if (a.weights_mode == SMCT_WEIGHTS_GAUSSIAN) {
         const float diff = ((const float*)a.y)[(long long)b * a.y_sb + f] - pr;
         sq = fmaf(diff, diff, sq);
@@ -426,7 +428,7 @@ __global__ void __launch_bounds__(NT) step_kernel(const StepArgs a) {
         if (f == ytok) py = pr;
       }
     }
-    if (lane == 0 && a.logw) {
+    if (lane == 0 && do_w) {
       a.logw[bp] = (a.weights_mode == SMCT_WEIGHTS_GAUSSIAN) ? ((-0.5f * sq) / a.sigma_obs) : (expf(py - mx) / se);
     }
   }
