@@ -1,0 +1,377 @@
+#!/usr/bin/env python
+"""bench.py — SMC-T forward + resample throughput (particle-steps/s) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # the CUDA path (this repo)
+    python bench.py --impl reference [--gpus N] [--steps K] ...    # reference-equivalent CPU path
+
+A "step" is one forward pass (SMC_Transformer.call: S particle-filter timesteps incl. resampling and
+the ancestor gather) over one batch of the workload.  Workload at N=1: BASELINE.json configs[3]
+(bs=4096, particles=1024, d_model=64, dff=256, seq_len=128), processed in resident chunks because the
+K/V/R state of the whole batch (412 GB) exceeds one GPU's HBM.  With N>1 every rank runs the same
+per-GPU batch on its own sequences (weak scaling; the forward needs no collective — all particles of
+a sequence live on one GPU).  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "particle-steps/sec (B*P*T) SMC-T fwd+resample"
+UNIT = "particle-steps/s"
+
+WORKLOADS = {
+    # name: (B, P, S, D, dff, F, alpha, var)
+    "c1": (32, 10, 24, 8, 8, 1, 0.8, 0.5),
+    "c2": (32, 100, 24, 8, 8, 1, 0.9, 0.3),
+    "c3": (256, 60, 24, 32, 32, 5, 0.9, 0.3),
+    "c4": (4096, 1024, 128, 64, 256, 1, 0.9, 0.3),
+}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=None, help="override the per-GPU batch (debug)")
+    ap.add_argument("--chunk", type=int, default=None, help="sequences per resident chunk")
+    ap.add_argument("--algo", default="auto", choices=["auto", "staged", "fused"])
+    ap.add_argument("--cpu-sample", type=int, default=None, help="sequences in the CPU baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload_desc(name, B, P, S, D, dff, F):
+    return ("%s: bs=%d particles=%d d_model=%d dff=%d seq_len=%d F=%d, 1 layer, 1 head, full_model, "
+            "gaussian weights, sigma2=0.5, sigma_obs=0.5" % (name.upper(), B, P, D, dff, S, F))
+
+
+# --------------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi during the timed region)
+# --------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "power_w_max": max(pw),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU arm: reference-equivalent eager restatement (oracle/ref_eager_torch.py) on the host cores
+# --------------------------------------------------------------------------------------------------
+def cpu_reference_run(wl, sample_B, steps, warmup):
+    """Times the reference-equivalent CPU path.  The only place bench.py executes oracle/ code."""
+    import torch
+    from oracle import ref_eager_torch as E
+    from oracle import smct_oracle as O
+    import smct_b200  # noqa: F401
+    from smct_b200 import utils
+    _, P, S, D, dff, F, alpha, var = WORKLOADS[wl]
+    cores = len(os.sched_getaffinity(0))
+    torch.set_num_threads(cores)
+    cfg = O.Config(B=sample_B, P=P, S=S, D=D, dff=dff, F_x=F, F_y=F)
+    p = utils.init_parameters(D, dff, F, F, sigma2=0.5)
+    tp = {k: torch.from_numpy(v.reshape(()) if k.startswith("logvar") else v) for k, v in p.items()}
+    x, y = utils.synthetic_ar1(sample_B, S, F, alpha, var)
+    tx, ty = torch.from_numpy(x), torch.from_numpy(y)
+    gen = torch.Generator().manual_seed(0)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        out = E.forward(cfg, tp, tx, ty, generator=gen)
+        float(E.loss_pyc(cfg, tp, out, ty))
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    t = sum(times) / len(times)
+    return {"value": sample_B * P * S / t, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "%d of the workload's sequences per step (B=%d, P=%d, S=%d, D=%d, dff=%d), %d timed step(s) after %d "
+                      "warm-up; op-for-op torch-CPU restatement of the reference's eager TF algorithm "
+                      "(TensorFlow is not installed)" % (sample_B, sample_B, P, S, D, dff, steps, warmup),
+            "s_per_step": t}
+
+
+def default_cpu_sample(wl):
+    return {"c4": 1, "c3": 16, "c2": 32, "c1": 32}[wl]
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    wl = args.workload
+    B, P, S, D, dff, F, _, _ = WORKLOADS[wl]
+    sample = args.cpu_sample or default_cpu_sample(wl)
+    r = cpu_reference_run(wl, sample, args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["s_per_step"] * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_desc(wl, B, P, S, D, dff, F), "sample_sequences_per_step": sample,
+                   "device": "host CPU, %d threads" % r["cores"]},
+        "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# --------------------------------------------------------------------------------------------------
+# the CUDA arm
+# --------------------------------------------------------------------------------------------------
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(algo, wl):
+    """dram bytes per forward launch from the committed ncu capture, if one exists for this algo/workload."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        with open(path) as f:
+            return json.load(f).get("%s:%s" % (algo, wl))
+    except Exception:
+        return None
+
+
+def run_b200(args):
+    import torch
+    import smct_b200
+    import smct_b200.functional as F_
+    from smct_b200 import utils
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the CUDA path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib = smct_b200.load_library()
+    dev = torch.device("cuda", local)
+
+    wl = args.workload
+    B, P, S, D, dff, F, alpha, var = WORKLOADS[wl]
+    if args.batch:
+        B = args.batch
+    p_host = utils.init_parameters(D, dff, F, F, sigma2=0.5)
+    params = {k: torch.as_tensor(v, device=dev) for k, v in p_host.items()}
+    # every rank works on its own sequences: global sequence index = rank*B + b (RNG keyed by it)
+    x_host, y_host = utils.synthetic_ar1(B, S, F, alpha, var, seed=1234 + rank)
+    x_pin = torch.from_numpy(x_host).pin_memory()
+    y_pin = torch.from_numpy(y_host).pin_memory()
+    x_dev, y_dev = x_pin.to(dev), y_pin.to(dev)
+
+    free_b, total_b = torch.cuda.mem_get_info()
+    state_per_seq = 3 * P * S * D * 4
+    fixed = 3 * B * P * S * F * 4 + (1 << 30)
+
+    def ws_per_seq(algo):
+        s1 = F_.make_shape(1, P, S, D, dff=dff, F_x=F, F_y=F, algo=algo)
+        s2 = F_.make_shape(2, P, S, D, dff=dff, F_x=F, F_y=F, algo=algo)
+        import ctypes
+        return lib.smct_workspace_bytes(ctypes.byref(s2)) - lib.smct_workspace_bytes(ctypes.byref(s1))
+
+    per_seq = state_per_seq + ws_per_seq(args.algo)
+    chunk = args.chunk or max(1, min(B, 512, int((free_b * 0.85 - fixed) // per_seq)))
+    n_chunks = (B + chunk - 1) // chunk
+
+    pred = torch.empty((B, P, S, F), dtype=torch.float32, device=dev)
+    pred_r = torch.empty((B, P, S, F), dtype=torch.float32, device=dev)
+    w = torch.empty((B, P, S), dtype=torch.float32, device=dev)
+    Kc = torch.empty((chunk, P, S, D), dtype=torch.float32, device=dev)
+    Vc = torch.empty_like(Kc)
+    Rc = torch.empty_like(Kc)
+    loss_sums = torch.zeros((n_chunks, 8), dtype=torch.float64, device=dev)
+    loss_host = torch.zeros((n_chunks, 8), dtype=torch.float64).pin_memory()
+
+    def forward_all(xd, yd, seed):
+        for c in range(n_chunks):
+            b0, b1 = c * chunk, min(B, (c + 1) * chunk)
+            n = b1 - b0
+            shape = F_.make_shape(n, P, S, D, dff=dff, F_x=F, F_y=F, algo=args.algo, b_global0=rank * B + b0)
+            out = dict(pred=pred[b0:b1], pred_resampl=pred_r[b0:b1], w=w[b0:b1], K=Kc[:n], V=Vc[:n], R=Rc[:n],
+                       loss_sums=loss_sums[c])
+            F_.forward(shape, params, xd[b0:b1], yd[b0:b1], seed=seed, want=("loss_sums",), out=out)
+
+    def loss_from_sums(ls):
+        # regression-era loss (pyc): mean 0.5*sum_n ||n||^2/sigma_n^2 + mean 0.5*||y-pred_resampl||^2/Sigma_obs
+        tot = ls.sum(0)
+        n = float(B) * P * S
+        return float((0.5 * (tot[0] + tot[1] + tot[2] + tot[3]) + 0.5 / 0.5 * tot[4]) / n)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- warm-up ----------------
+    for i in range(args.warmup):
+        forward_all(x_dev, y_dev, seed=100 + i)
+    barrier()
+
+    # ---------------- timed region: inputs resident in HBM ----------------
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    lib.smct_launch_count(1)
+    barrier()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    ev[0].record()
+    for i in range(args.steps):
+        forward_all(x_dev, y_dev, seed=200 + i)
+        ev[i + 1].record()
+    barrier()
+    launches = lib.smct_launch_count(1)
+    clocks = sampler.stop() if rank == 0 else None
+    step_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
+    total_ms = ev[0].elapsed_time(ev[args.steps])
+    tmax = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    total_ms_max = float(tmax.item())
+    psteps_per_gpu = float(B) * P * S * args.steps
+    value = psteps_per_gpu * world / (total_ms_max * 1e-3)
+    loss_dev = loss_from_sums(loss_sums.cpu())
+
+    # ---------------- end-to-end: host buffers -> H2D -> forward -> D2H loss ----------------
+    e2e = None
+    if not args.no_e2e:
+        e_steps = max(1, min(args.steps, 2))
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_wall0 = time.perf_counter()
+        e0.record()
+        for i in range(e_steps):
+            xd = x_pin.to(dev, non_blocking=True)
+            yd = y_pin.to(dev, non_blocking=True)
+            forward_all(xd, yd, seed=300 + i)
+            loss_host.copy_(loss_sums, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            loss_e2e = loss_from_sums(loss_host)
+        e1.record()
+        barrier()
+        wall_ms = (time.perf_counter() - t_wall0) * 1e3
+        e_ms = max(e0.elapsed_time(e1), wall_ms)
+        t2 = torch.tensor([e_ms], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+        e2e = {"value": float(B) * P * S * e_steps * world / (float(t2.item()) * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": int(x_pin.numel() * 4 + y_pin.numel() * 4),
+               "d2h_bytes_per_step": int(loss_host.numel() * 8), "steps": e_steps, "loss": loss_e2e,
+               "api": "smct_b200.functional.forward -> smct_forward (C-ABI), pinned host inputs, loss sums read back"}
+
+    # ---------------- CPU baseline (rank 0, N=1 only) ----------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        r = cpu_reference_run(wl, args.cpu_sample or default_cpu_sample(wl), 1, 0)
+        cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        bpp = utils.algorithmic_bytes_per_particle_step(D, S)
+        fwd_ms = (total_ms_max / args.steps) / n_chunks   # one smct_forward call (one chunk)
+        alg_bytes_per_launch = float(min(chunk, B)) * P * S * bpp
+        achieved = float(B) * P * S * bpp / (total_ms_max / args.steps * 1e-3) / 1e9
+        algo_used = args.algo
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_desc(wl, B, P, S, D, dff, F), "per_gpu_batch": B, "chunk_sequences": chunk,
+                       "chunks_per_step": n_chunks, "algo": algo_used, "rng": "device Philox4x32-10 + Box-Muller",
+                       "l2": "working set per chunk (%.1f GB state) >> 126 MB L2; no flush needed" % (chunk * state_per_seq / 1e9),
+                       "parallelism": "batch-sharded replicas, no collective in the forward"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": ncu_traffic(algo_used, wl), "peak_source": peak_src,
+                         "algorithmic_bytes_per_particle_step": bpp, "algorithmic_bytes_per_launch": alg_bytes_per_launch,
+                         "launch": "one smct_forward call over one chunk (%.1f ms avg, CUDA events)" % fwd_ms},
+            "cpu_baseline": cpu,
+            "e2e": e2e,
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "step_ms": step_ms,
+            "loss": loss_dev,
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_b200(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -100,6 +100,8 @@ typedef struct smct_io {
 int smct_abi_version(void);
 const char *smct_last_error(void);
 const char *smct_build_info(void);
+/* Number of CUDA kernels this library has launched in the process (reset!=0: return and zero). */
+long long smct_launch_count(int reset);
 
 /* Workspace (bytes, device memory) needed by smct_forward / smct_cell_step for this shape. */
 size_t smct_workspace_bytes(const smct_shape *shape);

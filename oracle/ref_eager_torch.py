@@ -1,0 +1,133 @@
+"""Reference-equivalent CPU restatement with torch-CPU ops — the `cpu_baseline` / `--impl reference` arm.
+
+*** TEST / MEASUREMENT INFRASTRUCTURE — NOT PRODUCT CODE. ***
+
+TensorFlow is not installed in this image (nor on the GPU box), so the reference's TF path cannot
+be timed.  This file restates, op for op, what the reference executes eagerly per timestep — same
+data-movement pattern, not an optimised one:
+  * inputs/targets tiled to P particles *before* the projection  (SMC_Transformer.py:166-172,193-194)
+  * 3 Dense on (B,P,1,D), randn noise, k - k_                     (self_attention_SMC.py:151-165)
+  * slice + concat to insert k_t, v_t (copies all of K and V)     (self_attention_SMC.py:111-116)
+  * matmul(q, K^T) over the full padded length S, -1e9 mask by concat, softmax, matmul(att, V) (:119-136)
+  * out Dense + noise, LN1/FFN/LN2, output Dense                  (SMC_TransformerCell.py:140-154)
+  * slice + concat to store r_t in R                              (SMC_TransformerCell.py:159-161)
+  * weights, categorical draw, concat[K,V,R] -> gather -> split   (SMC_TransformerCell.py:164-172)
+torch.set_num_threads(n) gives it all host cores, like TF's Eigen thread pool.
+With injected draws it reproduces oracle/smct_oracle.py (tests/test_oracle_cpu.py), which makes it a
+second, independently written restatement of the same reference lines.
+"""
+import math
+
+import torch
+
+
+def _ln(x, g, b, eps):
+    mean = x.mean(-1, keepdim=True)
+    var = (x - mean).square().mean(-1, keepdim=True)
+    inv = torch.rsqrt(var + eps) * g
+    return x * inv + (b - mean * inv)
+
+
+def _categorical(logits, u):
+    """TF CPU multinomial: fp64 running sum of exp(logit - max), upper_bound(u * total)."""
+    l64 = logits.double()
+    cdf = torch.cumsum(torch.exp(l64 - l64.max(dim=1, keepdim=True).values), dim=1)
+    tgt = u * cdf[:, -1:]
+    return torch.searchsorted(cdf, tgt, right=True).clamp_(max=logits.shape[1] - 1)
+
+
+@torch.no_grad()
+def forward(cfg, p, x_in, y, eps=None, u=None, generator=None):
+    """cfg: oracle Config (gaussian weights, linear input).  p: dict of torch CPU fp32 tensors.
+    x_in (B,S,F_x), y (B,S,F_y) torch CPU.  eps (4,S,B,P,D) / u (S,B,P) optional injected draws."""
+    B, P, S, D, H = cfg.B, cfg.P, cfg.S, cfg.D, cfg.H
+    Dh = D // H
+    # get_encoded_input: tile first, then project (SMC_Transformer.py:166-172)
+    inp = x_in.reshape(B, 1, S, cfg.F_x).repeat(1, P, 1, 1)
+    X = (inp @ p["W_in"] + p["b_in"]) * math.sqrt(D)                     # (B,P,S,D)
+    tgt = y.reshape(B, 1, S, cfg.F_y).repeat(1, P, 1, 1)
+    K = torch.zeros(B, P, S, D)
+    V = torch.zeros(B, P, S, D)
+    R = torch.zeros(B, P, S, D)
+    sk, sq, sv, sz = (torch.exp(0.5 * p["logvar_" + n]) for n in ("k", "q", "v", "z"))
+    r_list, w_list, i_list, nq_list, nz_list = [], [], [], [], []
+
+    def split_heads(a):  # self_attention_SMC.py:81-87
+        return a.reshape(B, P, -1, H, Dh).permute(0, 1, 3, 2, 4)
+
+    def concat_heads(a):  # :72-79
+        return a.permute(0, 1, 3, 2, 4).reshape(B, P, -1, D)
+
+    for t in range(S):
+        x = X[:, :, t:t + 1, :]
+        yt = tgt[:, :, t:t + 1, :]
+        x = _ln(x, p["ln1_g"], p["ln1_b"], cfg.ln_eps)
+        k_ = x @ p["Wk"] + p["bk"]
+        q_ = x @ p["Wq"] + p["bq"]
+        v_ = x @ p["Wv"] + p["bv"]
+        ek, eq, ev, ez = ((eps[i, t].unsqueeze(2) if eps is not None else torch.randn(B, P, 1, D, generator=generator))
+                          for i in range(4))
+        k = k_ + sk * ek
+        q = q_ + sq * eq
+        v = v_ + sv * ev
+        noise_q = q - q_
+        kh, qh, vh, Kh, Vh = split_heads(k), split_heads(q), split_heads(v), split_heads(K), split_heads(V)
+        Kh = torch.cat([Kh[:, :, :, :t], kh, Kh[:, :, :, t + 1:]], dim=3)
+        Vh = torch.cat([Vh[:, :, :, :t], vh, Vh[:, :, :, t + 1:]], dim=3)
+        logits = (qh @ Kh.transpose(-1, -2)) / math.sqrt(Dh)            # (B,P,H,1,S)
+        w_ = cfg.attn_window
+        if w_ is not None and t > w_:
+            logits = torch.cat([-1e9 * torch.ones(B, P, H, 1, t - w_), logits[..., t - w_:t + 1],
+                                -1e9 * torch.ones(B, P, H, 1, S - (t + 1))], dim=-1)
+        else:
+            logits = torch.cat([logits[..., :t + 1], -1e9 * torch.ones(B, P, H, 1, S - (t + 1))], dim=-1)
+        att = torch.softmax(logits, dim=-1)
+        zh = att @ Vh
+        z_ = concat_heads(zh)
+        K = concat_heads(Kh)
+        V = concat_heads(Vh)
+        z_proj = z_ @ p["Wz"] + p["bz"]
+        z = z_proj + sz * ez
+        noise_z = (z - z_) if cfg.noise_z_mode == "checkout" else (z - z_proj)
+        if cfg.full_model:
+            o = _ln(z + x, p["ln1_g"], p["ln1_b"], cfg.ln_eps)
+            r = torch.relu(o @ p["W1"] + p["b1"]) @ p["W2"] + p["b2"]
+            r = _ln(r + o, p["ln2_g"], p["ln2_b"], cfg.ln_eps)
+        else:
+            r = z
+        pred = r @ p["Wo"]
+        R = torch.cat([R[:, :, :t], r, R[:, :, t + 1:]], dim=2)
+        diff = yt - pred
+        logw = (-0.5 * (diff * diff).sum(-1).squeeze(-1)) / cfg.sigma_obs         # (B,P)
+        logw = logw - torch.logsumexp(logw, dim=1, keepdim=True)
+        ut = u[t] if u is not None else torch.rand(B, P, dtype=torch.float64, generator=generator)
+        i_t = _categorical(logw, ut)
+        if cfg.len_resampling is None or t < cfg.len_resampling:
+            KVR = torch.cat([K, V, R], dim=-1)                                     # SMC_TransformerCell.py:170-172
+            KVR = torch.gather(KVR, 1, i_t.reshape(B, P, 1, 1).expand(B, P, S, 3 * D))
+            K, V, R = torch.split(KVR, D, dim=-1)
+            K, V, R = K.contiguous(), V.contiguous(), R.contiguous()
+        r_list.append(r)
+        w_list.append(torch.exp(logw))
+        i_list.append(i_t)
+        nq_list.append(noise_q)
+        nz_list.append(noise_z)
+    R_unres = torch.cat(r_list, dim=2)
+    pred = R_unres @ p["Wo"]
+    pred_resampl = R @ p["Wo"]
+    noise_K = K - (X @ p["Wk"] + p["bk"])
+    noise_V = V - (X @ p["Wv"] + p["bv"])
+    return dict(pred=pred, pred_resampl=pred_resampl, K=K, V=V, R=R, w=torch.stack(w_list, dim=-1),
+                i_t=torch.stack(i_list), noise_q=torch.cat(nq_list, 2), noise_z=torch.cat(nz_list, 2),
+                noise_K_resampled=noise_K, noise_V_resampled=noise_V)
+
+
+def loss_pyc(cfg, p, out, y):
+    """Regression-era loss (pyc): mean_{b,p,s} sum_n 0.5||n||^2/sigma_n^2 + mean 0.5||y-pred_resampl||^2/Sigma_obs."""
+    B, S = cfg.B, cfg.S
+    tot = 0.0
+    for n, lv in (("noise_K_resampled", "logvar_k"), ("noise_q", "logvar_q"), ("noise_V_resampled", "logvar_v"),
+                  ("noise_z", "logvar_z")):
+        tot = tot + (0.5 * (out[n].square() / torch.exp(p[lv])).sum(-1)).mean()
+    diff = y.reshape(B, 1, S, cfg.F_y) - out["pred_resampl"]
+    return float(tot + (0.5 / cfg.sigma_obs) * diff.square().sum(-1).mean())

@@ -55,6 +55,7 @@ def _declare(lib):
         "smct_abi_version": (ctypes.c_int, []),
         "smct_last_error": (ctypes.c_char_p, []),
         "smct_build_info": (ctypes.c_char_p, []),
+        "smct_launch_count": (ctypes.c_longlong, [ctypes.c_int]),
         "smct_workspace_bytes": (ctypes.c_size_t, [SP]),
         "smct_forward": (ctypes.c_int, [SP, PP, IP, VP, ctypes.c_size_t, VP]),
         "smct_cell_step": (ctypes.c_int, [SP, PP, i32, VP, i32, VP, VP, VP, VP, u64, VP, VP, VP, VP, VP, VP, VP, VP,

@@ -6,6 +6,7 @@
 #include <string.h>
 #include <string>
 #include <algorithm>
+#include <atomic>
 
 #include "../../include/smct.h"
 #include "smct_common.cuh"
@@ -15,6 +16,7 @@
 namespace {
 
 thread_local std::string g_last_error;
+std::atomic<long long> g_launches{0};  // kernels launched by this library (bench.py's gpu_launches)
 
 int fail(int code, const char* fmt, ...) {
   char buf[512];
@@ -35,6 +37,7 @@ int fail(int code, const char* fmt, ...) {
 
 #define SMCT_LAUNCH_CHECK(name)                                                                  \
   do {                                                                                          \
+    g_launches.fetch_add(1, std::memory_order_relaxed);                                         \
     cudaError_t e__ = cudaGetLastError();                                                       \
     if (e__ != cudaSuccess)                                                                     \
       return fail(SMCT_ERR_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(e__));     \
@@ -283,6 +286,10 @@ const char* smct_build_info(void) {
 #define SMCT_STR(x) SMCT_STR2(x)
   return "libsmct_b200 abi " SMCT_STR(SMCT_ABI_VERSION) " | sm_100a | nvcc " SMCT_STR(__CUDACC_VER_MAJOR__) "." SMCT_STR(
       __CUDACC_VER_MINOR__) " | " __DATE__ " " __TIME__;
+}
+
+long long smct_launch_count(int reset) {
+  return reset ? g_launches.exchange(0) : g_launches.load();
 }
 
 size_t smct_workspace_bytes(const smct_shape* shape) {

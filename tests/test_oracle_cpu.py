@@ -114,3 +114,21 @@ def test_layer_norm_matches_torch():
     b = rng.standard_normal(33).astype(np.float32)
     ref = torch.nn.functional.layer_norm(torch.from_numpy(x), (33,), torch.from_numpy(g), torch.from_numpy(b), 1e-6).numpy()
     assert np.allclose(O.layer_norm(x, g, b, 1e-6), ref, rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("name", ["c3_b8", "heads3", "window2", "pyc_smoke"])
+def test_eager_torch_restatement_agrees_with_numpy_oracle(name):
+    """Two independently written restatements of the same reference lines (numpy oracle vs the
+    op-for-op torch-CPU port used as the CPU baseline) must agree on injected draws."""
+    torch = pytest.importorskip("torch")
+    from oracle import ref_eager_torch as E
+    c = CASES[name]
+    cfg = c["cfg"]
+    p, x_in, y, eps, u = util_cpu.make_case(cfg, seed=4, sigma2=c["sigma2"])
+    u, ora = util_cpu.screen_uniforms(cfg, p, x_in, y, eps, u, margin=1e-5)
+    tp = {k: torch.from_numpy(np.asarray(v, np.float32)) for k, v in p.items()}
+    out = E.forward(cfg, tp, torch.from_numpy(x_in), torch.from_numpy(y), torch.from_numpy(eps), torch.from_numpy(u))
+    assert np.array_equal(out["i_t"].numpy(), ora["i_t"])
+    for k in ("pred", "pred_resampl", "K", "V", "R", "w", "noise_q", "noise_z", "noise_K_resampled"):
+        assert np.allclose(out[k].numpy(), ora[k], rtol=2e-4, atol=2e-5), k
+    assert np.isclose(E.loss_pyc(cfg, tp, out, torch.from_numpy(y)), O.smc_loss(cfg, p, ora, y, "pyc")[0], rtol=1e-4)
