@@ -165,6 +165,18 @@ int smct_fill_uniform(uint64_t seed, int32_t t, int64_t b_global0, int32_t B, in
 int smct_sumsq_scaled(int64_t rows, int32_t D, const float *n, const float *logvar, int32_t logvar_dim,
                       double *out, void *stream);
 
+/* SMC_Transformer.get_encoded_input — SMC_Transformer.py:166-181 (decoder is None): embedding / projection
+ * times sqrt(d_model), one row per (b,s) (the particles of a sequence share it).  X (B,S,D) and/or
+ * X_ln = layernorm1(X) (B,S,D); either may be NULL. */
+int smct_encode(const smct_shape *shape, const smct_params *params, const void *x_in, float *X, float *X_ln,
+                void *stream);
+
+/* compute_classic_loss — SMC_Transformer.py:148-164 (sparse CE, checkout) / regression-era MSE form (pyc).
+ * out[0] += sum_{b,p,s} ||y[b,s]-pred[b,p,s]||^2 (gaussian; y (B,S,F_y) f32)
+ *        or sum_{b,p,s} CE(pred[b,p,s,:], y[b,s]) (classification; y (B,S) i32).  pred (B,P,S,F_y). */
+int smct_classic_loss(int32_t B, int32_t P, int32_t S, int32_t F_y, int32_t weights_mode, const float *pred,
+                      const void *y, double *out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

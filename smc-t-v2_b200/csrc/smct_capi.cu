@@ -502,4 +502,28 @@ int smct_sumsq_scaled(int64_t rows, int32_t D, const float* n, const float* logv
   return SMCT_OK;
 }
 
+int smct_encode(const smct_shape* shape, const smct_params* params, const void* x_in, float* X, float* X_ln,
+                void* stream) {
+  if (int rc = check_shape(shape)) return rc;
+  if (!params || !x_in || (!X && !X_ln)) return fail(SMCT_ERR_INVALID, "smct_encode: bad arguments");
+  const smct_shape& s = *shape;
+  smct::RowsArgs ra;
+  memset(&ra, 0, sizeof(ra));
+  ra.rows = (long long)s.B * s.S; ra.D = s.D; ra.Fx = s.F_x; ra.input_mode = s.input_mode; ra.do_ln = X_ln ? 1 : 0;
+  ra.sqrtD = sqrtf((float)s.D); ra.ln_eps = s.ln_eps; ra.x_in = x_in;
+  ra.W_in = params->W_in; ra.b_in = params->b_in; ra.ln_g = params->ln1_g; ra.ln_b = params->ln1_b;
+  ra.X = X; ra.xln = X_ln;
+  return launch_rows(ra, (cudaStream_t)stream);
+}
+
+int smct_classic_loss(int32_t B, int32_t P, int32_t S, int32_t F_y, int32_t weights_mode, const float* pred,
+                      const void* y, double* out, void* stream) {
+  if (B < 1 || P < 1 || S < 1 || F_y < 1 || !pred || !y || !out) return fail(SMCT_ERR_INVALID, "smct_classic_loss: bad arguments");
+  const long long rows = (long long)B * P * S;
+  smct::classic_loss_kernel<<<(int)std::min<long long>((rows + 255) / 256, 148 * 8), 256, 0, (cudaStream_t)stream>>>(
+      B, P, S, F_y, weights_mode, pred, y, out);
+  SMCT_LAUNCH_CHECK("classic_loss_kernel");
+  return SMCT_OK;
+}
+
 }  // extern "C"

@@ -72,8 +72,10 @@ __global__ void __launch_bounds__(128) rows_kernel(const RowsArgs a) {
       for (int d = threadIdx.x; d < D; d += blockDim.x) xl[d] = xs[d];
     }
     __syncthreads();
+    const bool proj = a.q_ || a.k_ || a.v_ || a.kx || a.vx;
     for (int d = threadIdx.x; d < D; d += blockDim.x) {
       if (a.xln) a.xln[row * D + d] = xl[d];
+      if (!proj) continue;
       float q = a.bq[d], k = a.bk[d], v = a.bv[d], kx = a.bk[d], vx = a.bv[d];
       for (int j = 0; j < D; ++j) {
         const float xj = xl[j], rj = xs[j];
@@ -648,6 +650,39 @@ __global__ void logweights_kernel(int B, int P, int Fy, int mode, float sigma_ob
       for (int f = 0; f < Fy; ++f) se += expf(pr[f] - mx);
       logw[bp] = expf(pr[((const int*)y)[b]] - mx) / se;
     }
+  }
+}
+
+// sum over (b,p,s) rows of ||y[b,s]-pred[b,p,s]||^2 (gaussian) or of the sparse cross-entropy (classification)
+__global__ void __launch_bounds__(256) classic_loss_kernel(int B, int P, int S, int Fy, int mode, const float* pred,
+                                                           const void* y, double* out) {
+  __shared__ double red[8];
+  const long long rows = (long long)B * P * S;
+  double acc = 0.0;
+  for (long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x; row < rows; row += (long long)gridDim.x * blockDim.x) {
+    const int s = (int)(row % S);
+    const int b = (int)(row / ((long long)P * S));
+    const float* pr = pred + row * Fy;
+    if (mode == SMCT_WEIGHTS_GAUSSIAN) {
+      const float* yr = (const float*)y + ((long long)b * S + s) * Fy;
+      float sq = 0.f;
+      for (int f = 0; f < Fy; ++f) { const float d = yr[f] - pr[f]; sq = fmaf(d, d, sq); }
+      acc += (double)sq;
+    } else {
+      float mx = -INFINITY;
+      for (int f = 0; f < Fy; ++f) mx = fmaxf(mx, pr[f]);
+      float se = 0.f;
+      for (int f = 0; f < Fy; ++f) se += expf(pr[f] - mx);
+      acc += (double)(mx + logf(se) - pr[((const int*)y)[(long long)b * S + s]]);
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(SMCT_FULL_MASK, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0;
+    for (int i = 0; i < 8; ++i) t += red[i];
+    atomicAdd(out, t);
   }
 }
 

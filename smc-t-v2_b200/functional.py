@@ -281,3 +281,27 @@ def sumsq_scaled(noise: torch.Tensor, logvar: torch.Tensor) -> torch.Tensor:
     check(lib.smct_sumsq_scaled(rows, D, _ptr(noise, torch.float32, "noise"), _ptr(lv, torch.float32, "logvar"),
                                 int(lv.numel()), _ptr(out), _stream()))
     return out
+
+
+def classic_loss_sum(pred: torch.Tensor, y: torch.Tensor, weights="gaussian") -> torch.Tensor:
+    """sum over (b,p,s) of ||y-pred||^2 (gaussian) or of the sparse cross-entropy (classification), fp64."""
+    require_cuda()
+    lib = _lib.load()
+    B, P, S, Fy = pred.shape
+    out = torch.zeros((1,), dtype=torch.float64, device=pred.device)
+    y_dtype = torch.int32 if weights == "classification" else torch.float32
+    check(lib.smct_classic_loss(B, P, S, Fy, WEIGHTS[weights], _ptr(pred, torch.float32, "pred"), _ptr(y, y_dtype, "y"),
+                                _ptr(out), _stream()))
+    return out
+
+
+def encode(shape: SmctShape, params, x_in: torch.Tensor, layer_norm=False) -> torch.Tensor:
+    """get_encoded_input: (B,S,D) encoded rows (optionally after layernorm1), shared by the particles."""
+    require_cuda()
+    lib = _lib.load()
+    X = torch.empty((shape.B, shape.S, shape.D), dtype=torch.float32, device=x_in.device)
+    x_dtype = torch.int32 if shape.input_mode == INPUT["embedding"] else torch.float32
+    ps = params_struct(params, shape)
+    check(lib.smct_encode(ctypes.byref(shape), ctypes.byref(ps), _ptr(x_in, x_dtype, "x_in"),
+                          None if layer_norm else _ptr(X), _ptr(X) if layer_norm else None, _stream()))
+    return X

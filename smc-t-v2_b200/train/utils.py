@@ -1,0 +1,52 @@
+"""Mirror of src/train/utils.py: training metric and the EM variance update (host-side bookkeeping on
+tensors the forward already produced; small reductions, not the hot path)."""
+import math
+
+import torch
+
+from .. import functional as F
+from ..models.SMC_Transformer.self_attention_SMC import logvar_vector
+
+
+def compute_categorical_cross_entropy(targets, preds, num_particles, attention_mask=None):
+    """train/utils.py:3-20: sparse CE of the particle-mean softmax (classification era)."""
+    if attention_mask is not None:
+        raise NotImplementedError("masked metric is out of scope")
+    probs = torch.softmax(preds, dim=-1).mean(dim=1, keepdim=True)              # (B,1,S,V)
+    B, _, S, V = probs.shape
+    t = torch.as_tensor(targets).reshape(B, 1, S, 1).to(probs.device, torch.int64)
+    return -(torch.log(torch.gather(probs, -1, t).clamp_min(1e-7))).mean()
+
+
+def compute_mse_metric(targets, preds):
+    """Regression-era metric (pyc train_step_SMC_T): MSE of the particle-mean prediction."""
+    t = torch.as_tensor(targets).to(preds.device, torch.float32)
+    return (preds.mean(dim=1, keepdim=True) - t).square().mean()
+
+
+def EM_update(err, logvar, it, EM_param):
+    """train/utils.py:48-51: var <- (1 - it^-a) exp(logvar) + it^-a err ; returns log(var)."""
+    g = float(it) ** (-EM_param)
+    return math.log((1.0 - g) * math.exp(logvar) + g * err)
+
+
+def EM(smc_transformer, it, EM_param):
+    """train/utils.py:22-46: per batch element j (in order) update the four scalar log-variances from the mean
+    squared noises.  Only scalar ('uni') variances, like the reference's EM mode."""
+    if not smc_transformer.cell.noise:
+        return smc_transformer
+    att = smc_transformer.cell.attention_smc
+    errs = {}
+    for n, noise in (("k", smc_transformer.noise_K_resampled), ("q", smc_transformer.noise_q),
+                     ("v", smc_transformer.noise_V_resampled), ("z", smc_transformer.noise_z)):
+        B = noise.shape[0]
+        per_b = torch.stack([F.sumsq_scaled(noise[j].contiguous(), torch.zeros(1, device=noise.device))[0]
+                             for j in range(B)]) / float(noise[0].numel())
+        errs[n] = per_b.cpu().tolist()
+    B = len(errs["k"])
+    for j in range(B):
+        for n in ("v", "k", "q", "z"):   # the reference's update order (:35-45)
+            var = getattr(att, "logvar_" + n)
+            cur = float(logvar_vector(var)[0].item())
+            var.assign(EM_update(errs[n][j], cur, it, EM_param))
+    return smc_transformer
