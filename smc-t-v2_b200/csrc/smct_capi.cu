@@ -272,6 +272,86 @@ int forward_staged(const smct_shape& s, const smct_params& pr, const smct_io& io
   return SMCT_OK;
 }
 
+// ------------------------------------------------------------------------------------------
+// fused forward: rows_kernel -> fused_forward_kernel (all S steps, one CTA per sequence)
+//                -> materialize_kernel -> final_kernel
+// ------------------------------------------------------------------------------------------
+int forward_fused(const smct_shape& s, const smct_params& pr, const smct_io& io, void* ws, size_t ws_bytes,
+                  cudaStream_t st) {
+  if (ws_bytes < smct::fused_forward_ws(s)) return fail(SMCT_ERR_WORKSPACE, "workspace %zu < required %zu", ws_bytes, smct::fused_forward_ws(s));
+  const int B = s.B, P = s.P, S = s.S, D = s.D;
+  const int Sa = (S + 7) / 8 * 8;
+  Carver c{(char*)ws, 0, ws_bytes};
+  const size_t BSD = (size_t)B * S * D;
+  float* xln = c.take<float>(BSD);
+  float* q_ = c.take<float>(BSD);
+  float* k_ = c.take<float>(BSD);
+  float* v_ = c.take<float>(BSD);
+  float* kx = c.take<float>(BSD);
+  float* vx = c.take<float>(BSD);
+  const size_t BSPD = (size_t)B * S * P * D;
+  float* Kp = c.take<float>(BSPD);
+  float* Vp = c.take<float>(BSPD);
+  float* Rp = c.take<float>(BSPD);
+  unsigned short* A0 = c.take<unsigned short>((size_t)B * P * Sa);
+  unsigned short* A1 = c.take<unsigned short>((size_t)B * P * Sa);
+  unsigned short* pos = c.take<unsigned short>((size_t)B * P);
+  int* aflag = c.take<int>((size_t)B);
+
+  if (io.loss_sums) SMCT_CUDA(cudaMemsetAsync(io.loss_sums, 0, 8 * sizeof(double), st));
+
+  smct::RowsArgs ra;
+  memset(&ra, 0, sizeof(ra));
+  ra.rows = (long long)B * S; ra.D = D; ra.Fx = s.F_x; ra.input_mode = s.input_mode; ra.do_ln = 1;
+  ra.sqrtD = sqrtf((float)D); ra.ln_eps = s.ln_eps; ra.x_in = io.x_in;
+  ra.W_in = pr.W_in; ra.b_in = pr.b_in; ra.ln_g = pr.ln1_g; ra.ln_b = pr.ln1_b;
+  ra.Wq = pr.Wq; ra.bq = pr.bq; ra.Wk = pr.Wk; ra.bk = pr.bk; ra.Wv = pr.Wv; ra.bv = pr.bv;
+  ra.xln = xln; ra.q_ = q_; ra.k_ = k_; ra.v_ = v_; ra.kx = kx; ra.vx = vx;
+  if (int rc = launch_rows(ra, st)) return rc;
+
+  smct::FusedArgs a;
+  memset(&a, 0, sizeof(a));
+  a.B = B; a.P = P; a.S = S; a.Sa = Sa; a.Fy = s.F_y;
+  a.attn_window = s.attn_window; a.len_resampling = s.len_resampling; a.noise_z_mode = s.noise_z_mode;
+  a.logvar_dim = s.logvar_dim; a.ln_eps = s.ln_eps; a.sigma_obs = s.sigma_obs;
+  a.b_global0 = s.b_global0; a.seed = io.seed;
+  a.xln = xln; a.q_ = q_; a.k_ = k_; a.v_ = v_;
+  a.y = (const float*)io.y; a.eps = io.eps; a.u = io.u; a.i_forced = io.i_forced;
+  a.p = pr;
+  a.Kp = Kp; a.Vp = Vp; a.Rp = Rp; a.A0 = A0; a.A1 = A1; a.pos_out = pos; a.aflag = aflag;
+  a.pred = io.pred; a.w = io.w; a.logw = io.logw; a.noise_q = io.noise_q; a.noise_z = io.noise_z;
+  a.i_out = io.i_out; a.loss_sums = io.loss_sums;
+  static bool attr_set = false;
+  const size_t smem = sizeof(smct::FusedSmem);
+  if (!attr_set) {
+    SMCT_CUDA(cudaFuncSetAttribute(smct::fused_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  smct::fused_forward_kernel<<<B, smct::FNT, smem, st>>>(a);
+  SMCT_LAUNCH_CHECK("fused_forward_kernel");
+
+  smct::MatArgs m;
+  memset(&m, 0, sizeof(m));
+  m.B = B; m.P = P; m.S = S; m.Sa = Sa; m.Kp = Kp; m.Vp = Vp; m.Rp = Rp; m.A0 = A0; m.A1 = A1; m.pos = pos; m.aflag = aflag;
+  m.K = io.K; m.V = io.V; m.R = io.R;
+  smct::materialize_kernel<<<(unsigned)((long long)B * P), 256, 0, st>>>(m);
+  SMCT_LAUNCH_CHECK("materialize_kernel");
+
+  smct::FinalArgs f;
+  memset(&f, 0, sizeof(f));
+  f.B = B; f.P = P; f.S = S; f.D = D; f.Fy = s.F_y; f.weights_mode = s.weights_mode; f.logvar_dim = s.logvar_dim;
+  f.K = io.K; f.V = io.V; f.R = io.R;
+  const bool want_noise = io.noise_K || io.noise_V || io.loss_sums;
+  f.kx = want_noise ? kx : nullptr; f.vx = want_noise ? vx : nullptr;
+  f.Wo = pr.Wo; f.logvar_k = pr.logvar_k; f.logvar_v = pr.logvar_v;
+  f.y = io.y;
+  f.pred_resampl = io.pred_resampl; f.noise_K = io.noise_K; f.noise_V = io.noise_V; f.loss_sums = io.loss_sums;
+  const long long nrows = (long long)B * P * S;
+  smct::final_kernel<<<(int)std::min<long long>((nrows + 7) / 8, 148LL * 32), 256, 0, st>>>(f);
+  SMCT_LAUNCH_CHECK("final_kernel");
+  return SMCT_OK;
+}
+
 }  // namespace
 
 // ==========================================================================================
@@ -309,10 +389,8 @@ int smct_forward(const smct_shape* shape, const smct_params* params, const smct_
   if (algo == SMCT_ALGO_AUTO) algo = smct::fused_supported(*shape, *io) ? SMCT_ALGO_FUSED : SMCT_ALGO_STAGED;
   if (algo == SMCT_ALGO_FUSED) {
     if (!smct::fused_supported(*shape, *io)) return fail(SMCT_ERR_UNSUPPORTED, "fused forward does not support this shape/io");
-    const char* err = nullptr;
-    int rc = smct::forward_fused(*shape, *params, *io, workspace, workspace_bytes, st, &err);
-    if (rc) return fail(rc, "%s", err ? err : "fused forward failed");
-    return SMCT_OK;
+    if (!io->y) return fail(SMCT_ERR_INVALID, "y (targets) required");
+    return forward_fused(*shape, *params, *io, workspace, workspace_bytes, st);
   }
   return forward_staged(*shape, *params, *io, workspace, workspace_bytes, st);
 }

@@ -30,3 +30,15 @@ CASES = {
 BIG_CASES = {
     "c4_b2_s16": dict(cfg=Config(B=2, P=1024, S=16, D=64, dff=256), sigma2=0.5),
 }
+
+# shapes served by the fused persistent kernel (d_model 64, dff 256, 1 head, full model, gaussian weights)
+FUSED_CASES = {
+    "f_p70": dict(cfg=Config(B=2, P=70, S=20, D=64, dff=256), sigma2=0.5),
+    "f_p1": dict(cfg=Config(B=3, P=1, S=5, D=64, dff=256), sigma2=0.5),
+    "f_p128_s9": dict(cfg=Config(B=2, P=128, S=9, D=64, dff=256, F_x=3, F_y=3), sigma2=0.3),
+    "f_p129_window": dict(cfg=Config(B=2, P=129, S=12, D=64, dff=256, attn_window=3), sigma2=0.5),
+    "f_stop_resampling": dict(cfg=Config(B=2, P=40, S=10, D=64, dff=256, len_resampling=4), sigma2=0.5),
+    "f_multi_pyc": dict(cfg=Config(B=2, P=33, S=8, D=64, dff=256, noise_z_mode="pyc", F_y=2), sigma2=0.2, multi=True),
+    "f_s1": dict(cfg=Config(B=2, P=16, S=1, D=64, dff=256), sigma2=0.5),
+    "f_p300": dict(cfg=Config(B=3, P=300, S=24, D=64, dff=256), sigma2=0.5),
+}

@@ -9,7 +9,7 @@ import smct_b200.functional as F
 from oracle import philox as PH
 from oracle import smct_oracle as O
 from tests import util
-from tests.cases import BIG_CASES, CASES
+from tests.cases import BIG_CASES, CASES, FUSED_CASES
 
 pytestmark = pytest.mark.gpu
 
@@ -203,14 +203,60 @@ def test_forward_free_running(name):
     util.compare_forward(cfg, p, dev, ora, y, check_indices=True)
 
 
+@pytest.mark.parametrize("algo", ["staged", "fused"])
 @pytest.mark.parametrize("name", sorted(BIG_CASES))
-def test_forward_c4_particle_count(name):
+def test_forward_c4_particle_count(name, algo):
     c = BIG_CASES[name]
     cfg = c["cfg"]
     p, x_in, y, eps, u = util.make_case(cfg, sigma2=c["sigma2"])
     u, ora = util.screen_uniforms(cfg, p, x_in, y, eps, u)
-    dev = util.run_device(cfg, p, x_in, y, eps, u, want=("i_out", "logw", "loss_sums"))
+    dev = util.run_device(cfg, p, x_in, y, eps, u, want=("i_out", "logw", "loss_sums", "noise_q", "noise_z", "noise_K"),
+                          algo=algo)
     util.compare_forward(cfg, p, dev, ora, y)
+
+
+FUSED_WANT = ("i_out", "logw", "noise_q", "noise_z", "noise_K", "noise_V", "loss_sums")
+
+
+@pytest.mark.parametrize("name", sorted(FUSED_CASES))
+def test_fused_forward_teacher_forced(name):
+    c = FUSED_CASES[name]
+    cfg = c["cfg"]
+    p, x_in, y, eps, u = util.make_case(cfg, sigma2=c["sigma2"], multi=c.get("multi", False))
+    ora = O.forward(cfg, p, x_in, y, eps, u)
+    dev = util.run_device(cfg, p, x_in, y, eps, u, i_forced=ora["i_t"], want=FUSED_WANT, algo="fused")
+    util.compare_forward(cfg, p, dev, ora, y)
+
+
+@pytest.mark.parametrize("name", sorted(FUSED_CASES))
+def test_fused_forward_free_running(name):
+    c = FUSED_CASES[name]
+    cfg = c["cfg"]
+    p, x_in, y, eps, u = util.make_case(cfg, seed=1, sigma2=c["sigma2"], multi=c.get("multi", False))
+    u, ora = util.screen_uniforms(cfg, p, x_in, y, eps, u)
+    dev = util.run_device(cfg, p, x_in, y, eps, u, want=FUSED_WANT, algo="fused")
+    util.compare_forward(cfg, p, dev, ora, y)
+
+
+def test_fused_device_rng_matches_oracle_with_same_draws():
+    cfg = FUSED_CASES["f_p300"]["cfg"]
+    p, x_in, y, _, _ = util.make_case(cfg, sigma2=0.5)
+    seed, b0 = 777, 12
+    eps = np.stack([np.stack([F.fill_noise(seed, w, t, b0, cfg.B, cfg.P, cfg.D).cpu().numpy() for t in range(cfg.S)])
+                    for w in range(4)])
+    u = np.stack([F.fill_uniform(seed, t, b0, cfg.B, cfg.P).cpu().numpy() for t in range(cfg.S)])
+    dev = util.run_device(cfg, p, x_in, y, None, None, seed=seed, b_global0=b0, want=FUSED_WANT, algo="fused")
+    ora = O.forward(cfg, p, x_in, y, eps, u, i_forced=dev["i_out"])
+    util.compare_forward(cfg, p, dev, ora, y)
+
+
+def test_auto_algo_selects_fused_and_rejects_unsupported():
+    import ctypes
+    from smct_b200 import _lib
+    cfg = CASES["c1"]["cfg"]
+    p, x_in, y, eps, u = util.make_case(cfg, sigma2=0.5)
+    with pytest.raises(_lib.SmctError):
+        util.run_device(cfg, p, x_in, y, eps, u, algo="fused")   # d_model 8 is not served by the fused kernel
 
 
 def test_forward_device_rng_matches_oracle_with_same_draws():
@@ -252,12 +298,13 @@ def test_golden_fixtures():
 
 
 # ----------------------------------------------------------------------------- size-independent properties
-def test_properties_at_scale():
+@pytest.mark.parametrize("algo", ["staged", "fused"])
+def test_properties_at_scale(algo):
     """Shapes the oracle cannot finish quickly: structural properties of the particle filter."""
     cfg = O.Config(B=8, P=1024, S=48, D=64, dff=256)
     p = O.init_params(cfg, sigma2=0.5)
     x_in, y = O.synthetic_series(cfg.B, cfg.S, 1, alpha=0.9, var=0.3)
-    dev = util.run_device(cfg, p, x_in, y, None, None, seed=7, want=("i_out", "logw", "noise_K", "noise_V"))
+    dev = util.run_device(cfg, p, x_in, y, None, None, seed=7, want=("i_out", "logw", "noise_K", "noise_V"), algo=algo)
     w = dev["w"].astype(np.float64)
     assert np.allclose(w.sum(axis=1), 1.0, atol=1e-4)              # normalised weights per (b, t)
     i = dev["i_out"]
@@ -272,5 +319,19 @@ def test_properties_at_scale():
     ref = dev["R"].astype(np.float64) @ p["Wo"].astype(np.float64)
     util.assert_close("pred_resampl", dev["pred_resampl"], ref)
     # re-running with the same seed is bit-identical (no atomics on the data path)
-    dev2 = util.run_device(cfg, p, x_in, y, None, None, seed=7, want=("i_out",))
+    dev2 = util.run_device(cfg, p, x_in, y, None, None, seed=7, want=("i_out",), algo=algo)
     assert np.array_equal(dev2["i_out"], dev["i_out"]) and np.array_equal(dev2["K"], dev["K"])
+
+
+def test_fused_and_staged_agree_at_scale():
+    """Same seed, both algorithms, C4 particle count: teacher-force the staged path with the fused path's
+    ancestors so that last-bit differences cannot fork the trajectories; everything must then agree."""
+    cfg = O.Config(B=4, P=1024, S=40, D=64, dff=256)
+    p = O.init_params(cfg, sigma2=0.5)
+    x_in, y = O.synthetic_series(cfg.B, cfg.S, 1, alpha=0.9, var=0.3)
+    fu = util.run_device(cfg, p, x_in, y, None, None, seed=11, want=("i_out", "logw", "loss_sums"), algo="fused")
+    st = util.run_device(cfg, p, x_in, y, None, None, seed=11, i_forced=fu["i_out"], want=("i_out", "logw", "loss_sums"),
+                         algo="staged")
+    for k in ("pred", "pred_resampl", "K", "V", "R", "w", "logw"):
+        util.assert_close(k, fu[k], st[k])
+    assert np.allclose(fu["loss_sums"][:5], st["loss_sums"][:5], rtol=2e-4)

@@ -63,6 +63,7 @@ def compare_forward(cfg, p, dev, ora, y, check_indices=True, loss_variant="check
             worst[k] = assert_close(k, dev[k], ora[k])
     if "noise_K" in dev:
         worst["noise_K"] = assert_close("noise_K", dev["noise_K"], ora["noise_K_resampled"])
+    if "noise_V" in dev:
         worst["noise_V"] = assert_close("noise_V", dev["noise_V"], ora["noise_V_resampled"])
     if "logw" in dev and cfg.noise:
         worst["logw"] = assert_close("logw", dev["logw"], ora["logw"])
