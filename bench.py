@@ -238,7 +238,10 @@ def run_b200(args):
         return lib.smct_workspace_bytes(ctypes.byref(s2)) - lib.smct_workspace_bytes(ctypes.byref(s1))
 
     per_seq = state_per_seq + ws_per_seq(args.algo)
-    chunk = args.chunk or max(1, min(B, 512, int((free_b * 0.85 - fixed) // per_seq)))
+    fit = max(1, int((free_b * 0.85 - fixed) // per_seq))
+    n_sm = torch.cuda.get_device_properties(local).multi_processor_count
+    # the fused forward runs one CTA (= one sequence) per SM: size chunks as whole waves of the SM count
+    chunk = args.chunk or (min(B, fit, 4 * n_sm) // n_sm * n_sm if min(B, fit) >= n_sm else min(B, fit))
     n_chunks = (B + chunk - 1) // chunk
 
     pred = torch.empty((B, P, S, F), dtype=torch.float32, device=dev)
