@@ -132,3 +132,35 @@ def test_eager_torch_restatement_agrees_with_numpy_oracle(name):
     for k in ("pred", "pred_resampl", "K", "V", "R", "w", "noise_q", "noise_z", "noise_K_resampled"):
         assert np.allclose(out[k].numpy(), ora[k], rtol=2e-4, atol=2e-5), k
     assert np.isclose(E.loss_pyc(cfg, tp, out, torch.from_numpy(y)), O.smc_loss(cfg, p, ora, y, "pyc")[0], rtol=1e-4)
+
+
+# ------------------------------------------------------------------------------------------------
+# the oracle against the outputs of the reference's OWN Python sources (run over oracle/tf_shim.py)
+# ------------------------------------------------------------------------------------------------
+from tests import ref_golden  # noqa: E402
+
+
+def _close(name, got, ref, rtol=1e-4):
+    got, ref = np.asarray(got, np.float64), np.asarray(ref, np.float64)
+    assert got.shape == ref.shape, (name, got.shape, ref.shape)
+    scale = np.abs(ref).max()
+    err = np.abs(got - ref)
+    assert (err <= rtol * np.abs(ref) + 0.1 * rtol * scale + 1e-30).all(), "%s: max err %g (scale %g)" % (name, err.max(), scale)
+
+
+@pytest.mark.parametrize("path", ref_golden.ref_files())
+def test_oracle_matches_reference_sources(path):
+    """numpy restatement == the reference's unmodified SMC_Transformer / cell / attention code (executed
+    over the TF shim) on the same weights and injected draws — including every quirk of the checkout."""
+    g, cfg, p, x_in, y = ref_golden.load(path)
+    out = O.forward(cfg, p, x_in, y, g["eps"], g["u"])
+    out["w_as_returned_by_reference"] = out["w"] if cfg.weights == "classification" else out["logits"].transpose(1, 2, 0)
+    ref_golden.compare(os.path.basename(path), out, g, _close)
+    variant = "checkout" if cfg.weights == "classification" else "pyc"
+    total, classic = O.smc_loss(cfg, p, out, y, variant)
+    assert np.isclose(total, float(g["loss_total"]), rtol=1e-4), (total, float(g["loss_total"]))
+    assert np.isclose(classic, float(g["loss_classic"]), rtol=1e-4)
+
+
+def test_reference_fixtures_exist():
+    assert len(ref_golden.ref_files()) >= 5
