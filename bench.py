@@ -262,11 +262,11 @@ def run_b200(args):
                        loss_sums=loss_sums[c])
             F_.forward(shape, params, xd[b0:b1], yd[b0:b1], seed=seed, want=("loss_sums",), out=out)
 
+    from smct_b200.distributed import loss_from_sums as _loss_from_sums
+
     def loss_from_sums(ls):
         # regression-era loss (pyc): mean 0.5*sum_n ||n||^2/sigma_n^2 + mean 0.5*||y-pred_resampl||^2/Sigma_obs
-        tot = ls.sum(0)
-        n = float(B) * P * S
-        return float((0.5 * (tot[0] + tot[1] + tot[2] + tot[3]) + 0.5 / 0.5 * tot[4]) / n)
+        return _loss_from_sums(ls.sum(0).tolist(), float(B) * P * S, sigma_obs=0.5, variant="pyc")[0]
 
     def barrier():
         if dist is not None:

@@ -335,3 +335,27 @@ def test_fused_and_staged_agree_at_scale():
     for k in ("pred", "pred_resampl", "K", "V", "R", "w", "logw"):
         util.assert_close(k, fu[k], st[k])
     assert np.allclose(fu["loss_sums"][:5], st["loss_sums"][:5], rtol=2e-4)
+
+
+@pytest.mark.parametrize("algo", ["staged", "fused"])
+def test_shards_reproduce_the_full_batch(algo):
+    """Batch sharding: running contiguous shards with b_global0 = first global sequence
+    index reproduces the unsharded forward bit for bit (device RNG is keyed by the global index)."""
+    from smct_b200.distributed import shard_range
+    cfg = O.Config(B=6, P=256, S=12, D=64, dff=256)
+    p = O.init_params(cfg, sigma2=0.5)
+    x_in, y = O.synthetic_series(cfg.B, cfg.S, 1, alpha=0.9, var=0.3)
+    full = util.run_device(cfg, p, x_in, y, None, None, seed=99, b_global0=100, want=("i_out", "loss_sums"), algo=algo)
+    sums = np.zeros(8)
+    for r in range(4):
+        b0, b1 = shard_range(cfg.B, r, 4)
+        if b1 == b0:
+            continue
+        sc = O.Config(B=b1 - b0, P=cfg.P, S=cfg.S, D=cfg.D, dff=cfg.dff)
+        part = util.run_device(sc, p, x_in[b0:b1], y[b0:b1], None, None, seed=99, b_global0=100 + b0,
+                               want=("i_out", "loss_sums"), algo=algo)
+        assert np.array_equal(part["i_out"], full["i_out"][:, b0:b1])
+        for k in ("pred", "K", "R", "w"):
+            assert np.array_equal(part[k], full[k][b0:b1]), k
+        sums += part["loss_sums"]
+    assert np.allclose(sums[:5], full["loss_sums"][:5], rtol=1e-6)
