@@ -171,6 +171,11 @@ int smct_sumsq_scaled(int64_t rows, int32_t D, const float *n, const float *logv
 int smct_encode(const smct_shape *shape, const smct_params *params, const void *x_in, float *X, float *X_ln,
                 void *stream);
 
+/* Self-test of the tcgen05 building blocks used by the fused forward's dense part: D (128,64) = A (128,64) · W (64,64)
+ * (W in Keras layout [in][out]) computed as a three-term bf16 split on the tensor cores with fp32 TMEM
+ * accumulation.  scratch: >= 16 KB of device memory. */
+int smct_tc_selftest(const float *A, const float *W, float *D, void *scratch, void *stream);
+
 /* compute_classic_loss — SMC_Transformer.py:148-164 (sparse CE, checkout) / regression-era MSE form (pyc).
  * out[0] += sum_{b,p,s} ||y[b,s]-pred[b,p,s]||^2 (gaussian; y (B,S,F_y) f32)
  *        or sum_{b,p,s} CE(pred[b,p,s,:], y[b,s]) (classification; y (B,S) i32).  pred (B,P,S,F_y). */

@@ -68,6 +68,7 @@ def _declare(lib):
         "smct_fill_noise": (ctypes.c_int, [u64, i32, i32, i64, i32, i32, i32, VP, VP]),
         "smct_fill_uniform": (ctypes.c_int, [u64, i32, i64, i32, i32, VP, VP]),
         "smct_sumsq_scaled": (ctypes.c_int, [i64, i32, VP, VP, i32, VP, VP]),
+        "smct_tc_selftest": (ctypes.c_int, [VP, VP, VP, VP, VP]),
         "smct_encode": (ctypes.c_int, [SP, PP, VP, VP, VP, VP]),
         "smct_classic_loss": (ctypes.c_int, [i32, i32, i32, i32, i32, VP, VP, VP, VP]),
     }

@@ -12,6 +12,7 @@
 #include "smct_common.cuh"
 #include "smct_staged.cuh"
 #include "smct_fused.cuh"
+#include "smct_tc.cuh"
 
 namespace {
 
@@ -592,6 +593,22 @@ int smct_encode(const smct_shape* shape, const smct_params* params, const void* 
   ra.W_in = params->W_in; ra.b_in = params->b_in; ra.ln_g = params->ln1_g; ra.ln_b = params->ln1_b;
   ra.X = X; ra.xln = X_ln;
   return launch_rows(ra, (cudaStream_t)stream);
+}
+
+int smct_tc_selftest(const float* A, const float* W, float* D, void* scratch, void* stream) {
+  if (!A || !W || !D || !scratch) return fail(SMCT_ERR_INVALID, "smct_tc_selftest: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  smct::tc_weight_prep_kernel<<<16, 256, 0, st>>>(W, nullptr, nullptr, 0, (unsigned char*)scratch);
+  SMCT_LAUNCH_CHECK("tc_weight_prep_kernel");
+  const int smem = 2 * smct::tc::A_PART_BYTES + 2 * smct::tc::B_PART_BYTES + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SMCT_CUDA(cudaFuncSetAttribute(smct::tc_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  smct::tc_selftest_kernel<<<1, 128, smem, st>>>(A, (const unsigned char*)scratch, D);
+  SMCT_LAUNCH_CHECK("tc_selftest_kernel");
+  return SMCT_OK;
 }
 
 int smct_classic_loss(int32_t B, int32_t P, int32_t S, int32_t F_y, int32_t weights_mode, const float* pred,

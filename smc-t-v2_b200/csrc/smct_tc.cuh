@@ -1,0 +1,226 @@
+// smct_tc.cuh — tcgen05 (5th-gen tensor core) building blocks for the dense part of the fused forward:
+// shared-memory operand layout, descriptors, TMEM allocation, MMA issue / commit, TMEM loads.
+//
+// Precision: the parity bar is 1e-4 relative in fp32, which single-pass bf16/tf32 operands cannot meet.
+// Every fp32 operand x is split into two bf16 terms  h = bf16(x), m = bf16(x - h)  (16 mantissa bits) and a
+// product A·B is issued as three kind::f16 MMAs into the same fp32 TMEM accumulator:
+//     A_h·B_h + A_m·B_h + A_h·B_m          (the dropped A_m·B_m term is O(2^-16) relative).
+//
+// Operand layout (K-major, no swizzle; cute "INTERLEAVE" canonical layout ((8,n),2):((1,SBO),LBO) in 16-byte
+// units): a tile of R rows x 64 k-values of bf16 is stored as 8x8 "core matrices" of 128 bytes
+// (8 rows x 16 bytes); element (r,k) lives at byte
+//     (r/8)*1024 + (k/8)*128 + (r%8)*16 + (k%8)*2        -> LBO = 128 B (next core along K), SBO = 1024 B.
+// One tcgen05.mma consumes K = 16 (two cores along K): K-step j starts at byte offset 256*j.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace smct {
+namespace tc {
+
+constexpr uint32_t LBO_BYTES = 128;
+constexpr uint32_t SBO_BYTES = 1024;
+constexpr uint32_t A_PART_BYTES = 128 * 64 * 2;   // one bf16 part (h or m) of a 128x64 A tile: 16 KB
+constexpr uint32_t B_PART_BYTES = 64 * 64 * 2;    // one bf16 part of a 64(N)x64(K) B block: 8 KB
+
+__device__ __forceinline__ uint32_t operand_offset(int r, int k) {
+  return (uint32_t)((r >> 3) * (int)SBO_BYTES + (k >> 3) * (int)LBO_BYTES + (r & 7) * 16 + (k & 7) * 2);
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// 64-bit shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30),
+// SBO>>4 [32,46), version=1 [46,48), layout type 0 (no swizzle) [61,64).
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((LBO_BYTES >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((SBO_BYTES >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+
+// instruction descriptor (cute::UMMA::InstrDescriptor) for kind::f16: D=F32, A=B=BF16, K-major both,
+// N>>3 at [17,23), M>>4 at [24,29).
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// D[128 x N] (+)= A[128 x 64] * B[N x 64]^T with the three-term bf16 split.  One thread issues.
+// a_base / b_base: shared addresses of the h part; the m part follows at +A_PART_BYTES / +b_part_bytes.
+__device__ __forceinline__ void mma_block_bf16x3(uint32_t tmem_d, uint32_t a_base, uint32_t b_base, uint32_t b_part_bytes,
+                                                 uint32_t idesc, bool accumulate) {
+  const uint32_t a_off[3] = {0u, A_PART_BYTES, 0u};
+  const uint32_t b_off[3] = {0u, 0u, b_part_bytes};
+#pragma unroll
+  for (int term = 0; term < 3; ++term) {
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      const uint64_t da = make_desc(a_base + a_off[term] + 256u * ks);
+      const uint64_t db = make_desc(b_base + b_off[term] + 256u * ks);
+      mma_f16(tmem_d, da, db, idesc, (accumulate || term > 0 || ks > 0) ? 1u : 0u);
+    }
+  }
+}
+
+__device__ __forceinline__ void commit(uint64_t* mbar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(mbar)) : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint64_t* mbar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(mbar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+// bounded wait: traps instead of hanging the GPU if the MMA never commits
+__device__ __forceinline__ void mbar_wait(uint64_t* mbar, uint32_t parity) {
+  const uint32_t addr = smem_u32(mbar);
+  uint32_t done = 0;
+  for (uint32_t spin = 0; spin < (1u << 22); ++spin) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) return;
+  }
+  __trap();
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// TMEM allocation: executed by ONE full warp; the base address is written to *slot (shared memory)
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+// 32 consecutive fp32 columns of this thread's TMEM lane (warp w reads lanes 32*(w%4)..+31; lane i of the warp = row)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float v[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// split 4 consecutive fp32 values into packed bf16 h and m parts (8 bytes each)
+__device__ __forceinline__ void split4(const float x[4], uint2& h, uint2& m) {
+  __nv_bfloat16 hb[4], mb[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    hb[i] = __float2bfloat16_rn(x[i]);
+    mb[i] = __float2bfloat16_rn(x[i] - __bfloat162float(hb[i]));
+  }
+  h.x = (uint32_t)__bfloat16_as_ushort(hb[0]) | ((uint32_t)__bfloat16_as_ushort(hb[1]) << 16);
+  h.y = (uint32_t)__bfloat16_as_ushort(hb[2]) | ((uint32_t)__bfloat16_as_ushort(hb[3]) << 16);
+  m.x = (uint32_t)__bfloat16_as_ushort(mb[0]) | ((uint32_t)__bfloat16_as_ushort(mb[1]) << 16);
+  m.y = (uint32_t)__bfloat16_as_ushort(mb[2]) | ((uint32_t)__bfloat16_as_ushort(mb[3]) << 16);
+}
+
+// write 4 consecutive k-values (k0 % 4 == 0) of row r into an A operand tile (h part at base, m part at base + A_PART_BYTES)
+__device__ __forceinline__ void store_a4(unsigned char* base, int r, int k0, const float x[4]) {
+  uint2 h, m;
+  split4(x, h, m);
+  const uint32_t off = operand_offset(r, k0);
+  *reinterpret_cast<uint2*>(base + off) = h;
+  *reinterpret_cast<uint2*>(base + A_PART_BYTES + off) = m;
+}
+
+}  // namespace tc
+
+// ------------------------------------------------------------------------------------------
+// weight preparation: fp32 Keras kernels -> bf16 (h,m) blocks in the operand layout.
+// Block b (16 KB: h part 8 KB then m part 8 KB) holds B[n][k] for n,k < 64:
+//   b = 0        : Wz[k][n]
+//   b = 1 + 2c   : W1[k][64c + n]
+//   b = 2 + 2c   : W2[64c + k][n]          (c = 0..dff/64-1)
+// ------------------------------------------------------------------------------------------
+__global__ void tc_weight_prep_kernel(const float* Wz, const float* W1, const float* W2, int dff, unsigned char* out) {
+  const int nblk = 1 + 2 * (dff / 64);
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < nblk * 4096; idx += gridDim.x * blockDim.x) {
+    const int b = idx >> 12, n = (idx >> 6) & 63, k = idx & 63;
+    float w;
+    if (b == 0) w = Wz[k * 64 + n];
+    else if (b & 1) w = W1[k * dff + ((b - 1) >> 1) * 64 + n];
+    else w = W2[(((b - 2) >> 1) * 64 + k) * 64 + n];
+    const __nv_bfloat16 h = __float2bfloat16_rn(w);
+    const __nv_bfloat16 m = __float2bfloat16_rn(w - __bfloat162float(h));
+    unsigned char* blk = out + (size_t)b * 2 * tc::B_PART_BYTES;
+    const uint32_t off = tc::operand_offset(n, k);
+    *reinterpret_cast<__nv_bfloat16*>(blk + off) = h;
+    *reinterpret_cast<__nv_bfloat16*>(blk + tc::B_PART_BYTES + off) = m;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// self-test: D[128x64] = A[128x64] * W[64x64] (W in Keras layout [k][n]) through tcgen05 + TMEM.
+// One CTA of 128 threads.  Validates descriptors, operand layout, TMEM lane mapping and fences.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) tc_selftest_kernel(const float* A, const unsigned char* wblk, float* D) {
+  extern __shared__ __align__(1024) unsigned char tsm[];
+  unsigned char* As = tsm;                             // 32 KB (h,m)
+  unsigned char* Bs = tsm + 2 * tc::A_PART_BYTES;      // 16 KB (h,m)
+  __shared__ __align__(8) uint64_t mbar;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, wid = tid >> 5;
+  if (wid == 0) tc::tmem_alloc(&tmem_slot, 64);
+  if (tid == 0) { tc::mbar_init(&mbar, 1); tc::fence_mbar_init(); }
+  // A tile: thread = row
+  for (int k0 = 0; k0 < 64; k0 += 4) {
+    float x[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) x[e] = A[tid * 64 + k0 + e];
+    tc::store_a4(As, tid, k0, x);
+  }
+  for (int i = tid; i < (int)(2 * tc::B_PART_BYTES / 16); i += 128)
+    reinterpret_cast<uint4*>(Bs)[i] = reinterpret_cast<const uint4*>(wblk)[i];
+  tc::fence_async_smem();
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+  if (tid == 0) {
+    tc::mma_block_bf16x3(tmem, tc::smem_u32(As), tc::smem_u32(Bs), tc::B_PART_BYTES, tc::make_idesc(128, 64), false);
+    tc::commit(&mbar);
+  }
+  tc::mbar_wait(&mbar, 0);
+  tc::fence_after_sync();
+  for (int half = 0; half < 2; ++half) {
+    float v[32];
+    tc::tmem_ld32(tmem + ((uint32_t)(32 * wid) << 16) + 32 * half, v);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) D[tid * 64 + 32 * half + i] = v[i];
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (wid == 0) tc::tmem_dealloc(tmem, 64);
+}
+
+}  // namespace smct

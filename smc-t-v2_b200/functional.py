@@ -305,3 +305,13 @@ def encode(shape: SmctShape, params, x_in: torch.Tensor, layer_norm=False) -> to
     check(lib.smct_encode(ctypes.byref(shape), ctypes.byref(ps), _ptr(x_in, x_dtype, "x_in"),
                           None if layer_norm else _ptr(X), _ptr(X) if layer_norm else None, _stream()))
     return X
+
+
+def tc_selftest(A: torch.Tensor, W: torch.Tensor) -> torch.Tensor:
+    """(128,64) @ (64,64) on tcgen05 with the three-term bf16 split (building block of the fused dense part)."""
+    require_cuda()
+    lib = _lib.load()
+    D = torch.empty((128, 64), dtype=torch.float32, device=A.device)
+    scratch = torch.empty(16384, dtype=torch.uint8, device=A.device)
+    check(lib.smct_tc_selftest(_ptr(A, torch.float32, "A"), _ptr(W, torch.float32, "W"), _ptr(D), _ptr(scratch), _stream()))
+    return D
