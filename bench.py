@@ -47,7 +47,7 @@ def parse():
     ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=None, help="override the per-GPU batch (debug)")
     ap.add_argument("--chunk", type=int, default=None, help="sequences per resident chunk")
-    ap.add_argument("--algo", default="auto", choices=["auto", "staged", "fused"])
+    ap.add_argument("--algo", default="auto", choices=["auto", "staged", "fused", "fused_ffma"])
     ap.add_argument("--cpu-sample", type=int, default=None, help="sequences in the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")

@@ -40,7 +40,8 @@ enum {
 enum { SMCT_WEIGHTS_GAUSSIAN = 0, SMCT_WEIGHTS_CLASSIFICATION = 1 };
 enum { SMCT_NOISE_Z_CHECKOUT = 0, SMCT_NOISE_Z_PYC = 1 };
 enum { SMCT_INPUT_LINEAR = 0, SMCT_INPUT_EMBEDDING = 1, SMCT_INPUT_ENCODED = 2 };
-enum { SMCT_ALGO_AUTO = 0, SMCT_ALGO_STAGED = 1, SMCT_ALGO_FUSED = 2 };
+/* FUSED: persistent kernel, dense part on tcgen05; FUSED_FFMA: same kernel structure, dense part on CUDA cores */
+enum { SMCT_ALGO_AUTO = 0, SMCT_ALGO_STAGED = 1, SMCT_ALGO_FUSED = 2, SMCT_ALGO_FUSED_FFMA = 3 };
 
 /* Problem shape + switches.  Mirrors the constructor arguments of
  * SMC_Transformer(d_model, output_size, seq_len, full_model, dff, num_heads, attn_window)
@@ -172,8 +173,8 @@ int smct_encode(const smct_shape *shape, const smct_params *params, const void *
                 void *stream);
 
 /* Self-test of the tcgen05 building blocks used by the fused forward's dense part: D (128,64) = A (128,64) · W (64,64)
- * (W in Keras layout [in][out]) computed as a three-term bf16 split on the tensor cores with fp32 TMEM
- * accumulation.  scratch: >= 16 KB of device memory. */
+ * (W in Keras layout [in][out]) computed as a three-term fp16 split (exact power-of-two scaling) on the tensor cores with fp32 TMEM
+ * accumulation.  scratch: >= 16 KB + 256 B of device memory. */
 int smct_tc_selftest(const float *A, const float *W, float *D, void *scratch, void *stream);
 
 /* compute_classic_loss — SMC_Transformer.py:148-164 (sparse CE, checkout) / regression-era MSE form (pyc).

@@ -13,6 +13,7 @@
 #include "smct_staged.cuh"
 #include "smct_fused.cuh"
 #include "smct_tc.cuh"
+#include "smct_fused_tc.cuh"
 
 namespace {
 
@@ -278,7 +279,7 @@ int forward_staged(const smct_shape& s, const smct_params& pr, const smct_io& io
 //                -> materialize_kernel -> final_kernel
 // ------------------------------------------------------------------------------------------
 int forward_fused(const smct_shape& s, const smct_params& pr, const smct_io& io, void* ws, size_t ws_bytes,
-                  cudaStream_t st) {
+                  cudaStream_t st, bool use_tc) {
   if (ws_bytes < smct::fused_forward_ws(s)) return fail(SMCT_ERR_WORKSPACE, "workspace %zu < required %zu", ws_bytes, smct::fused_forward_ws(s));
   const int B = s.B, P = s.P, S = s.S, D = s.D;
   const int Sa = (S + 7) / 8 * 8;
@@ -298,8 +299,13 @@ int forward_fused(const smct_shape& s, const smct_params& pr, const smct_io& io,
   unsigned short* A1 = c.take<unsigned short>((size_t)B * P * Sa);
   unsigned short* pos = c.take<unsigned short>((size_t)B * P);
   int* aflag = c.take<int>((size_t)B);
+  unsigned char* wtc = c.take<unsigned char>((size_t)(1 + 2 * (smct::FF / smct::FD)) * 16384 + 256);
 
   if (io.loss_sums) SMCT_CUDA(cudaMemsetAsync(io.loss_sums, 0, 8 * sizeof(double), st));
+  if (use_tc) {
+    smct::tc_weight_prep_kernel<<<1, 1024, 0, st>>>(pr.Wz, pr.W1, pr.W2, pr.b1, pr.ln1_g, pr.ln1_b, smct::FF, wtc);
+    SMCT_LAUNCH_CHECK("tc_weight_prep_kernel");
+  }
 
   smct::RowsArgs ra;
   memset(&ra, 0, sizeof(ra));
@@ -322,14 +328,22 @@ int forward_fused(const smct_shape& s, const smct_params& pr, const smct_io& io,
   a.Kp = Kp; a.Vp = Vp; a.Rp = Rp; a.A0 = A0; a.A1 = A1; a.pos_out = pos; a.aflag = aflag;
   a.pred = io.pred; a.w = io.w; a.logw = io.logw; a.noise_q = io.noise_q; a.noise_z = io.noise_z;
   a.i_out = io.i_out; a.loss_sums = io.loss_sums;
+  a.wtc = wtc;
   static bool attr_set = false;
-  const size_t smem = sizeof(smct::FusedSmem);
   if (!attr_set) {
-    SMCT_CUDA(cudaFuncSetAttribute(smct::fused_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SMCT_CUDA(cudaFuncSetAttribute(smct::fused_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)sizeof(smct::FusedSmem)));
+    SMCT_CUDA(cudaFuncSetAttribute(smct::fused_tc_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)sizeof(smct::FusedTcSmem) + 1024));
     attr_set = true;
   }
-  smct::fused_forward_kernel<<<B, smct::FNT, smem, st>>>(a);
-  SMCT_LAUNCH_CHECK("fused_forward_kernel");
+  if (use_tc) {
+    smct::fused_tc_forward_kernel<<<B, smct::FNT, sizeof(smct::FusedTcSmem) + 1024, st>>>(a);
+    SMCT_LAUNCH_CHECK("fused_tc_forward_kernel");
+  } else {
+    smct::fused_forward_kernel<<<B, smct::FNT, sizeof(smct::FusedSmem), st>>>(a);
+    SMCT_LAUNCH_CHECK("fused_forward_kernel");
+  }
 
   smct::MatArgs m;
   memset(&m, 0, sizeof(m));
@@ -388,10 +402,10 @@ int smct_forward(const smct_shape* shape, const smct_params* params, const smct_
   cudaStream_t st = (cudaStream_t)stream;
   int algo = shape->algo;
   if (algo == SMCT_ALGO_AUTO) algo = smct::fused_supported(*shape, *io) ? SMCT_ALGO_FUSED : SMCT_ALGO_STAGED;
-  if (algo == SMCT_ALGO_FUSED) {
+  if (algo == SMCT_ALGO_FUSED || algo == SMCT_ALGO_FUSED_FFMA) {
     if (!smct::fused_supported(*shape, *io)) return fail(SMCT_ERR_UNSUPPORTED, "fused forward does not support this shape/io");
     if (!io->y) return fail(SMCT_ERR_INVALID, "y (targets) required");
-    return forward_fused(*shape, *params, *io, workspace, workspace_bytes, st);
+    return forward_fused(*shape, *params, *io, workspace, workspace_bytes, st, algo == SMCT_ALGO_FUSED);
   }
   return forward_staged(*shape, *params, *io, workspace, workspace_bytes, st);
 }
@@ -598,7 +612,7 @@ int smct_encode(const smct_shape* shape, const smct_params* params, const void* 
 int smct_tc_selftest(const float* A, const float* W, float* D, void* scratch, void* stream) {
   if (!A || !W || !D || !scratch) return fail(SMCT_ERR_INVALID, "smct_tc_selftest: bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
-  smct::tc_weight_prep_kernel<<<16, 256, 0, st>>>(W, nullptr, nullptr, 0, (unsigned char*)scratch);
+  smct::tc_weight_prep_kernel<<<1, 1024, 0, st>>>(W, nullptr, nullptr, nullptr, nullptr, nullptr, 0, (unsigned char*)scratch);
   SMCT_LAUNCH_CHECK("tc_weight_prep_kernel");
   const int smem = 2 * smct::tc::A_PART_BYTES + 2 * smct::tc::B_PART_BYTES + 1024;
   static bool attr_set = false;

@@ -40,6 +40,7 @@ struct FusedArgs {
   const double* u;                   // optional (S,B,P)
   const int* i_forced;               // optional (S,B,P)
   smct_params p;
+  const unsigned char* wtc;          // bf16 (h,m) weight blocks in the tcgen05 operand layout (tensor-core variant)
   float *Kp, *Vp, *Rp;               // (B,S,P,64) slot-major physical rows
   unsigned short *A0, *A1;           // (B,P,Sa) ancestry rows, ping-pong
   unsigned short* pos_out;           // (B,P)  final position of each logical particle
@@ -49,7 +50,7 @@ struct FusedArgs {
   double* loss_sums;
 };
 
-struct FusedSmem {
+struct FusedCommon {           // per-sequence bookkeeping shared by both fused kernels
   double cdf[FPMAX];
   float lw[FPMAX];
   unsigned int keys[FPMAX];
@@ -59,6 +60,10 @@ struct FusedSmem {
   float ivar[4][FD];         // exp(-logvar)
   float red[64];
   double dred[2];
+};
+
+struct FusedSmem {
+  FusedCommon c;
   float Zs[FTILE * FLD];
   float Os[FTILE * FLD];
   float Hs[FTILE * FLD];
@@ -112,6 +117,113 @@ __device__ __forceinline__ void wblock_commit(float* WBbuf, int tid, const float
   for (int h = 0; h < 2; ++h) reinterpret_cast<float4*>(WBbuf)[tid + h * FNT] = wr[h];
 }
 
+// logsumexp normalise, TF-CPU categorical draw (fp64 sequential CDF in logical particle order), then the
+// genealogy update: sort the new particles by the position of their ancestor (tree order) and rewrite the
+// ancestry rows.  Called by all threads of the CTA once per timestep.
+__device__ __forceinline__ void fused_resample_update(FusedCommon& c, const FusedArgs& a, int b, int t,
+                                                      unsigned short*& Acur, unsigned short*& Anxt, int& cur_is_A0) {
+  const int tid = threadIdx.x;
+  const int P = a.P, S = a.S, Sa = a.Sa;
+  const long long bP = (long long)b * P;
+  // =========================== weights, categorical draw (TF CPU semantics) ===========================
+  float m1 = -INFINITY;
+  for (int p = tid; p < P; p += FNT) { const float v = c.lw[p]; if (isfinite(v)) m1 = fmaxf(m1, v); }
+  m1 = block_max(m1, c.red);
+  float s1 = 0.f;
+  for (int p = tid; p < P; p += FNT) s1 += expf(c.lw[p] - m1);
+  s1 = block_sum(s1, c.red);
+  const float lse = m1 + logf(s1);
+  float m2 = -INFINITY;
+  for (int p = tid; p < P; p += FNT) { const float v = c.lw[p] - lse; if (isfinite(v)) m2 = fmaxf(m2, v); }
+  m2 = block_max(m2, c.red);
+  for (int p = tid; p < P; p += FNT) {
+    const float raw = c.lw[p];
+    const float lg = raw - lse;
+    if (a.w) a.w[(bP + p) * S + t] = expf(lg);
+    if (a.logw) a.logw[((long long)t * a.B + b) * P + p] = raw;
+    c.cdf[p] = isfinite(lg) ? exp((double)lg - (double)m2) : 0.0;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double run = 0.0;
+    for (int p = 0; p < P; ++p) { run += c.cdf[p]; c.cdf[p] = run; }
+    c.dred[0] = run;
+  }
+  __syncthreads();
+  const double total = c.dred[0];
+  for (int p = tid; p < P; p += FNT) {
+    const long long ti = ((long long)t * a.B + b) * P + p;
+    int idx;
+    if (a.i_forced) {
+      idx = a.i_forced[ti];
+    } else {
+      const double uu = a.u ? a.u[ti]
+                            : philox_uniform(a.seed, (uint32_t)t,
+                                             (unsigned long long)(a.b_global0 + b) * (unsigned long long)P + p);
+      const double target = uu * total;
+      int lo = 0, hi = P;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (c.cdf[mid] <= target) lo = mid + 1; else hi = mid;
+      }
+      idx = min(lo, P - 1);
+    }
+    if (a.i_out) a.i_out[ti] = idx;
+    c.anc[p] = (unsigned short)idx;
+  }
+  __syncthreads();
+
+  // =========================== genealogy update ===========================
+  const bool resample_now = (a.len_resampling < 0) || (t < a.len_resampling);
+  if (resample_now) {
+    // sort the new particles by the position of their ancestor (ties by logical id): tree order is preserved
+    int np2 = 1;
+    while (np2 < P) np2 <<= 1;
+    for (int p = tid; p < np2; p += FNT)
+      c.keys[p] = (p < P) ? (((unsigned int)c.pos[c.anc[p]] << 16) | (unsigned int)p) : 0xFFFFFFFFu;
+    __syncthreads();
+    for (int k = 2; k <= np2; k <<= 1) {
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int i = tid; i < np2; i += FNT) {
+          const int ixj = i ^ j;
+          if (ixj > i) {
+            const unsigned int x = c.keys[i], yv = c.keys[ixj];
+            const bool up = ((i & k) == 0);
+            if ((x > yv) == up) { c.keys[i] = yv; c.keys[ixj] = x; }
+          }
+        }
+        __syncthreads();
+      }
+    }
+    for (int qn = tid; qn < P; qn += FNT) {
+      const unsigned int key = c.keys[qn];
+      c.src[qn] = (unsigned short)(key >> 16);
+      c.Lq[qn] = (unsigned short)(key & 0xFFFFu);
+    }
+    __syncthreads();
+    for (int qn = tid; qn < P; qn += FNT) c.pos[c.Lq[qn]] = (unsigned short)qn;
+    // ancestry rows: Anxt[q'][0..t) = Acur[src[q']][0..t) ; Anxt[q'][t] = src[q']   (8 slots = one uint4)
+    const int nch = (t >> 3) + 1;
+    for (int i = tid; i < P * nch; i += FNT) {
+      const int qn = i / nch, ch = i - qn * nch;
+      const int sq = c.src[qn];
+      uint4 v = *reinterpret_cast<const uint4*>(Acur + (long long)sq * Sa + 8 * ch);
+      if ((t >> 3) == ch) {  // patch slot t (little-endian: element e is half (e&1) of word (e>>1))
+        const int e = t & 7;
+        unsigned int wv = (e >> 1) == 0 ? v.x : ((e >> 1) == 1 ? v.y : ((e >> 1) == 2 ? v.z : v.w));
+        wv = (e & 1) ? ((wv & 0x0000FFFFu) | ((unsigned int)sq << 16)) : ((wv & 0xFFFF0000u) | (unsigned int)sq);
+        if ((e >> 1) == 0) v.x = wv; else if ((e >> 1) == 1) v.y = wv; else if ((e >> 1) == 2) v.z = wv; else v.w = wv;
+      }
+      *reinterpret_cast<uint4*>(Anxt + (long long)qn * Sa + 8 * ch) = v;
+    }
+    unsigned short* tmp = Acur; Acur = Anxt; Anxt = tmp;
+    cur_is_A0 ^= 1;
+  } else {
+    for (int qn = tid; qn < P; qn += FNT) Acur[(long long)qn * Sa + t] = (unsigned short)qn;
+  }
+  __syncthreads();
+}
+
 __global__ void __launch_bounds__(FNT, 1) fused_forward_kernel(const FusedArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   FusedSmem& sm = *reinterpret_cast<FusedSmem*>(smem_raw);
@@ -130,13 +242,13 @@ __global__ void __launch_bounds__(FNT, 1) fused_forward_kernel(const FusedArgs a
   const int pl = tid >> 2, l4 = tid & 3;        // attention: particle-in-tile, lane-in-particle
   double dloss_q = 0.0, dloss_z = 0.0;          // thread 0 only
 
-  for (int i = tid; i < P; i += FNT) { sm.Lq[i] = (unsigned short)i; sm.pos[i] = (unsigned short)i; }
+  for (int i = tid; i < P; i += FNT) { sm.c.Lq[i] = (unsigned short)i; sm.c.pos[i] = (unsigned short)i; }
   if (tid < 4 * FD) {
     const int which = tid >> 6, d = tid & 63;
     const float* lv = which == 0 ? a.p.logvar_k : (which == 1 ? a.p.logvar_q : (which == 2 ? a.p.logvar_v : a.p.logvar_z));
     const float v = lv[a.logvar_dim > 1 ? d : 0];
-    sm.stdtab[which][d] = expf(0.5f * v);
-    sm.ivar[which][d] = expf(-v);
+    sm.c.stdtab[which][d] = expf(0.5f * v);
+    sm.c.ivar[which][d] = expf(-v);
   }
   __syncthreads();
 
@@ -145,7 +257,7 @@ __global__ void __launch_bounds__(FNT, 1) fused_forward_kernel(const FusedArgs a
     if (tid < 4 * FD) {
       const int which = tid >> 6, d = tid & 63;
       const float* src = which == 0 ? a.xln : (which == 1 ? a.q_ : (which == 2 ? a.k_ : a.v_));
-      sm.rowbuf[which][d] = src[((long long)b * S + t) * FD + d];
+      sm.c.rowbuf[which][d] = src[((long long)b * S + t) * FD + d];
     }
     __syncthreads();
     float loss_q = 0.f, loss_z = 0.f;
@@ -161,7 +273,7 @@ __global__ void __launch_bounds__(FNT, 1) fused_forward_kernel(const FusedArgs a
         const int q = q0 + pl;
         const bool act = pl < np;
         const int qc = act ? q : (P - 1);
-        const int L = sm.Lq[qc];
+        const int L = sm.c.Lq[qc];
         const unsigned long long gbp = (unsigned long long)(a.b_global0 + b) * (unsigned long long)P + L;
         const long long lrow = ((bP + L) * S + t) * FD;              // logical (b,L,t) row of (B,P,S,64) outputs
         const long long prow = ((long long)t * P + qc) * FD;         // physical slot-t row of this particle
@@ -169,9 +281,9 @@ __global__ void __launch_bounds__(FNT, 1) fused_forward_kernel(const FusedArgs a
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int c = l4 + 4 * i, d0 = 4 * c;
-          const float4 q_0 = *reinterpret_cast<const float4*>(&sm.rowbuf[1][d0]);
-          const float4 k_0 = *reinterpret_cast<const float4*>(&sm.rowbuf[2][d0]);
-          const float4 v_0 = *reinterpret_cast<const float4*>(&sm.rowbuf[3][d0]);
+          const float4 q_0 = *reinterpret_cast<const float4*>(&sm.c.rowbuf[1][d0]);
+          const float4 k_0 = *reinterpret_cast<const float4*>(&sm.c.rowbuf[2][d0]);
+          const float4 v_0 = *reinterpret_cast<const float4*>(&sm.c.rowbuf[3][d0]);
           float ek[4], eq[4], ev[4], ez[4];
           if (a.eps) {
             const long long BPD = (long long)a.B * P * FD;
@@ -196,12 +308,12 @@ __global__ void __launch_bounds__(FNT, 1) fused_forward_kernel(const FusedArgs a
           float ko[4], qo[4], vo[4], nq[4], nz0[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            ko[e] = __fadd_rn(kin[e], __fmul_rn(sm.stdtab[0][d0 + e], ek[e]));
-            qo[e] = __fadd_rn(qin[e], __fmul_rn(sm.stdtab[1][d0 + e], eq[e]));
-            vo[e] = __fadd_rn(vin[e], __fmul_rn(sm.stdtab[2][d0 + e], ev[e]));
+            ko[e] = __fadd_rn(kin[e], __fmul_rn(sm.c.stdtab[0][d0 + e], ek[e]));
+            qo[e] = __fadd_rn(qin[e], __fmul_rn(sm.c.stdtab[1][d0 + e], eq[e]));
+            vo[e] = __fadd_rn(vin[e], __fmul_rn(sm.c.stdtab[2][d0 + e], ev[e]));
             nq[e] = qo[e] - qin[e];
-            nz0[e] = __fmul_rn(sm.stdtab[3][d0 + e], ez[e]);
-            loss_q = act ? fmaf(nq[e] * nq[e], sm.ivar[1][d0 + e], loss_q) : loss_q;
+            nz0[e] = __fmul_rn(sm.c.stdtab[3][d0 + e], ez[e]);
+            loss_q = act ? fmaf(nq[e] * nq[e], sm.c.ivar[1][d0 + e], loss_q) : loss_q;
           }
           qv[i] = make_float4(qo[0], qo[1], qo[2], qo[3]);
           *reinterpret_cast<float4*>(&sm.Os[pl * FLD + d0]) = make_float4(nz0[0], nz0[1], nz0[2], nz0[3]);
@@ -294,12 +406,12 @@ __global__ void __launch_bounds__(FNT, 1) fused_forward_kernel(const FusedArgs a
           const float zp = acc[i][j] + __ldg(a.p.bz + n);
           const float z = __fadd_rn(zp, sm.Os[r * FLD + n]);
           nzv[j] = (a.noise_z_mode == SMCT_NOISE_Z_CHECKOUT) ? (z - sm.Zs[r * FLD + n]) : (z - zp);
-          loss_z = act ? fmaf(nzv[j] * nzv[j], sm.ivar[3][n], loss_z) : loss_z;
-          zo[j] = z + sm.rowbuf[0][n];
+          loss_z = act ? fmaf(nzv[j] * nzv[j], sm.c.ivar[3][n], loss_z) : loss_z;
+          zo[j] = z + sm.c.rowbuf[0][n];
         }
         *reinterpret_cast<float4*>(&sm.Os[r * FLD + 4 * tx]) = make_float4(zo[0], zo[1], zo[2], zo[3]);
         if (act && a.noise_z) {
-          const int L = sm.Lq[q0 + r];
+          const int L = sm.c.Lq[q0 + r];
           *reinterpret_cast<float4*>(a.noise_z + ((bP + L) * S + t) * FD + 4 * tx) = make_float4(nzv[0], nzv[1], nzv[2], nzv[3]);
         }
       }
@@ -361,7 +473,7 @@ __global__ void __launch_bounds__(FNT, 1) fused_forward_kernel(const FusedArgs a
       // ---- r = LN2(r_pre); R row store; output layer; log-weight: warp per row ----
       for (int r = wid; r < np; r += FNT / 32) {
         const int q = q0 + r;
-        const int L = sm.Lq[q];
+        const int L = sm.c.Lq[q];
         const float v0 = sm.Zs[r * FLD + lane], v1 = sm.Zs[r * FLD + lane + 32];
         const float mean = warp_sum(v0 + v1) * (1.0f / FD);
         const float c0 = v0 - mean, c1 = v1 - mean;
@@ -380,7 +492,7 @@ __global__ void __launch_bounds__(FNT, 1) fused_forward_kernel(const FusedArgs a
           const float diff = a.y[((long long)b * S + t) * Fy + f] - pr;
           sq = fmaf(diff, diff, sq);
         }
-        if (lane == 0) sm.lw[L] = (-0.5f * sq) / a.sigma_obs;
+        if (lane == 0) sm.c.lw[L] = (-0.5f * sq) / a.sigma_obs;
       }
       __syncthreads();
     }  // tiles
@@ -388,113 +500,17 @@ __global__ void __launch_bounds__(FNT, 1) fused_forward_kernel(const FusedArgs a
     // =========================== loss partials of this step ===========================
     if (a.loss_sums) {
       const float sq = warp_sum(loss_q), sz = warp_sum(loss_z);
-      if (lane == 0) { sm.red[wid] = sq; sm.red[16 + wid] = sz; }
+      if (lane == 0) { sm.c.red[wid] = sq; sm.c.red[16 + wid] = sz; }
       __syncthreads();
       if (tid == 0) {
-        for (int i = 0; i < 16; ++i) { dloss_q += (double)sm.red[i]; dloss_z += (double)sm.red[16 + i]; }
+        for (int i = 0; i < 16; ++i) { dloss_q += (double)sm.c.red[i]; dloss_z += (double)sm.c.red[16 + i]; }
       }
     }
 
-    // =========================== weights, categorical draw (TF CPU semantics) ===========================
-    float m1 = -INFINITY;
-    for (int p = tid; p < P; p += FNT) { const float v = sm.lw[p]; if (isfinite(v)) m1 = fmaxf(m1, v); }
-    m1 = block_max(m1, sm.red);
-    float s1 = 0.f;
-    for (int p = tid; p < P; p += FNT) s1 += expf(sm.lw[p] - m1);
-    s1 = block_sum(s1, sm.red);
-    const float lse = m1 + logf(s1);
-    float m2 = -INFINITY;
-    for (int p = tid; p < P; p += FNT) { const float v = sm.lw[p] - lse; if (isfinite(v)) m2 = fmaxf(m2, v); }
-    m2 = block_max(m2, sm.red);
-    for (int p = tid; p < P; p += FNT) {
-      const float raw = sm.lw[p];
-      const float lg = raw - lse;
-      if (a.w) a.w[(bP + p) * S + t] = expf(lg);
-      if (a.logw) a.logw[((long long)t * a.B + b) * P + p] = raw;
-      sm.cdf[p] = isfinite(lg) ? exp((double)lg - (double)m2) : 0.0;
-    }
-    __syncthreads();
-    if (tid == 0) {
-      double run = 0.0;
-      for (int p = 0; p < P; ++p) { run += sm.cdf[p]; sm.cdf[p] = run; }
-      sm.dred[0] = run;
-    }
-    __syncthreads();
-    const double total = sm.dred[0];
-    for (int p = tid; p < P; p += FNT) {
-      const long long ti = ((long long)t * a.B + b) * P + p;
-      int idx;
-      if (a.i_forced) {
-        idx = a.i_forced[ti];
-      } else {
-        const double uu = a.u ? a.u[ti]
-                              : philox_uniform(a.seed, (uint32_t)t,
-                                               (unsigned long long)(a.b_global0 + b) * (unsigned long long)P + p);
-        const double target = uu * total;
-        int lo = 0, hi = P;
-        while (lo < hi) {
-          const int mid = (lo + hi) >> 1;
-          if (sm.cdf[mid] <= target) lo = mid + 1; else hi = mid;
-        }
-        idx = min(lo, P - 1);
-      }
-      if (a.i_out) a.i_out[ti] = idx;
-      sm.anc[p] = (unsigned short)idx;
-    }
-    __syncthreads();
-
-    // =========================== genealogy update ===========================
-    const bool resample_now = (a.len_resampling < 0) || (t < a.len_resampling);
-    if (resample_now) {
-      // sort the new particles by the position of their ancestor (ties by logical id): tree order is preserved
-      int np2 = 1;
-      while (np2 < P) np2 <<= 1;
-      for (int p = tid; p < np2; p += FNT)
-        sm.keys[p] = (p < P) ? (((unsigned int)sm.pos[sm.anc[p]] << 16) | (unsigned int)p) : 0xFFFFFFFFu;
-      __syncthreads();
-      for (int k = 2; k <= np2; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-          for (int i = tid; i < np2; i += FNT) {
-            const int ixj = i ^ j;
-            if (ixj > i) {
-              const unsigned int x = sm.keys[i], yv = sm.keys[ixj];
-              const bool up = ((i & k) == 0);
-              if ((x > yv) == up) { sm.keys[i] = yv; sm.keys[ixj] = x; }
-            }
-          }
-          __syncthreads();
-        }
-      }
-      for (int qn = tid; qn < P; qn += FNT) {
-        const unsigned int key = sm.keys[qn];
-        sm.src[qn] = (unsigned short)(key >> 16);
-        sm.Lq[qn] = (unsigned short)(key & 0xFFFFu);
-      }
-      __syncthreads();
-      for (int qn = tid; qn < P; qn += FNT) sm.pos[sm.Lq[qn]] = (unsigned short)qn;
-      // ancestry rows: Anxt[q'][0..t) = Acur[src[q']][0..t) ; Anxt[q'][t] = src[q']   (8 slots = one uint4)
-      const int nch = (t >> 3) + 1;
-      for (int i = tid; i < P * nch; i += FNT) {
-        const int qn = i / nch, ch = i - qn * nch;
-        const int sq = sm.src[qn];
-        uint4 v = *reinterpret_cast<const uint4*>(Acur + (long long)sq * Sa + 8 * ch);
-        if ((t >> 3) == ch) {  // patch slot t (little-endian: element e is half (e&1) of word (e>>1))
-          const int e = t & 7;
-          unsigned int wv = (e >> 1) == 0 ? v.x : ((e >> 1) == 1 ? v.y : ((e >> 1) == 2 ? v.z : v.w));
-          wv = (e & 1) ? ((wv & 0x0000FFFFu) | ((unsigned int)sq << 16)) : ((wv & 0xFFFF0000u) | (unsigned int)sq);
-          if ((e >> 1) == 0) v.x = wv; else if ((e >> 1) == 1) v.y = wv; else if ((e >> 1) == 2) v.z = wv; else v.w = wv;
-        }
-        *reinterpret_cast<uint4*>(Anxt + (long long)qn * Sa + 8 * ch) = v;
-      }
-      unsigned short* tmp = Acur; Acur = Anxt; Anxt = tmp;
-      cur_is_A0 ^= 1;
-    } else {
-      for (int qn = tid; qn < P; qn += FNT) Acur[(long long)qn * Sa + t] = (unsigned short)qn;
-    }
-    __syncthreads();
+    fused_resample_update(sm.c, a, b, t, Acur, Anxt, cur_is_A0);
   }  // timesteps
 
-  for (int p = tid; p < P; p += FNT) a.pos_out[bP + p] = sm.pos[p];
+  for (int p = tid; p < P; p += FNT) a.pos_out[bP + p] = sm.c.pos[p];
   if (tid == 0) {
     a.aflag[b] = cur_is_A0;
     if (a.loss_sums) { atomicAdd(a.loss_sums + 1, dloss_q); atomicAdd(a.loss_sums + 3, dloss_z); }
@@ -549,6 +565,7 @@ inline size_t fused_forward_ws(const smct_shape& s) {
   n += 2 * fused_align((size_t)s.B * s.P * Sa * sizeof(unsigned short));
   n += fused_align((size_t)s.B * s.P * sizeof(unsigned short));
   n += fused_align((size_t)s.B * sizeof(int));
+  n += fused_align((size_t)(1 + 2 * (FF / FD)) * 16384 + 256);   // tensor-core weight blocks + header
   return n + 1024;
 }
 

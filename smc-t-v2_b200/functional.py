@@ -312,6 +312,6 @@ def tc_selftest(A: torch.Tensor, W: torch.Tensor) -> torch.Tensor:
     require_cuda()
     lib = _lib.load()
     D = torch.empty((128, 64), dtype=torch.float32, device=A.device)
-    scratch = torch.empty(16384, dtype=torch.uint8, device=A.device)
+    scratch = torch.empty(16384 + 256, dtype=torch.uint8, device=A.device)
     check(lib.smct_tc_selftest(_ptr(A, torch.float32, "A"), _ptr(W, torch.float32, "W"), _ptr(D), _ptr(scratch), _stream()))
     return D

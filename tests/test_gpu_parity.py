@@ -203,7 +203,7 @@ def test_forward_free_running(name):
     util.compare_forward(cfg, p, dev, ora, y, check_indices=True)
 
 
-@pytest.mark.parametrize("algo", ["staged", "fused"])
+@pytest.mark.parametrize("algo", ["staged", "fused", "fused_ffma"])
 @pytest.mark.parametrize("name", sorted(BIG_CASES))
 def test_forward_c4_particle_count(name, algo):
     c = BIG_CASES[name]
@@ -218,34 +218,40 @@ def test_forward_c4_particle_count(name, algo):
 FUSED_WANT = ("i_out", "logw", "noise_q", "noise_z", "noise_K", "noise_V", "loss_sums")
 
 
+FUSED_ALGOS = ["fused", "fused_ffma"]
+
+
+@pytest.mark.parametrize("algo", FUSED_ALGOS)
 @pytest.mark.parametrize("name", sorted(FUSED_CASES))
-def test_fused_forward_teacher_forced(name):
+def test_fused_forward_teacher_forced(name, algo):
     c = FUSED_CASES[name]
     cfg = c["cfg"]
     p, x_in, y, eps, u = util.make_case(cfg, sigma2=c["sigma2"], multi=c.get("multi", False))
     ora = O.forward(cfg, p, x_in, y, eps, u)
-    dev = util.run_device(cfg, p, x_in, y, eps, u, i_forced=ora["i_t"], want=FUSED_WANT, algo="fused")
+    dev = util.run_device(cfg, p, x_in, y, eps, u, i_forced=ora["i_t"], want=FUSED_WANT, algo=algo)
     util.compare_forward(cfg, p, dev, ora, y)
 
 
+@pytest.mark.parametrize("algo", FUSED_ALGOS)
 @pytest.mark.parametrize("name", sorted(FUSED_CASES))
-def test_fused_forward_free_running(name):
+def test_fused_forward_free_running(name, algo):
     c = FUSED_CASES[name]
     cfg = c["cfg"]
     p, x_in, y, eps, u = util.make_case(cfg, seed=1, sigma2=c["sigma2"], multi=c.get("multi", False))
     u, ora = util.screen_uniforms(cfg, p, x_in, y, eps, u)
-    dev = util.run_device(cfg, p, x_in, y, eps, u, want=FUSED_WANT, algo="fused")
+    dev = util.run_device(cfg, p, x_in, y, eps, u, want=FUSED_WANT, algo=algo)
     util.compare_forward(cfg, p, dev, ora, y)
 
 
-def test_fused_device_rng_matches_oracle_with_same_draws():
+@pytest.mark.parametrize("algo", FUSED_ALGOS)
+def test_fused_device_rng_matches_oracle_with_same_draws(algo):
     cfg = FUSED_CASES["f_p300"]["cfg"]
     p, x_in, y, _, _ = util.make_case(cfg, sigma2=0.5)
     seed, b0 = 777, 12
     eps = np.stack([np.stack([F.fill_noise(seed, w, t, b0, cfg.B, cfg.P, cfg.D).cpu().numpy() for t in range(cfg.S)])
                     for w in range(4)])
     u = np.stack([F.fill_uniform(seed, t, b0, cfg.B, cfg.P).cpu().numpy() for t in range(cfg.S)])
-    dev = util.run_device(cfg, p, x_in, y, None, None, seed=seed, b_global0=b0, want=FUSED_WANT, algo="fused")
+    dev = util.run_device(cfg, p, x_in, y, None, None, seed=seed, b_global0=b0, want=FUSED_WANT, algo=algo)
     ora = O.forward(cfg, p, x_in, y, eps, u, i_forced=dev["i_out"])
     util.compare_forward(cfg, p, dev, ora, y)
 
@@ -298,7 +304,7 @@ def test_golden_fixtures():
 
 
 # ----------------------------------------------------------------------------- size-independent properties
-@pytest.mark.parametrize("algo", ["staged", "fused"])
+@pytest.mark.parametrize("algo", ["staged", "fused", "fused_ffma"])
 def test_properties_at_scale(algo):
     """Shapes the oracle cannot finish quickly: structural properties of the particle filter."""
     cfg = O.Config(B=8, P=1024, S=48, D=64, dff=256)
@@ -337,7 +343,7 @@ def test_fused_and_staged_agree_at_scale():
     assert np.allclose(fu["loss_sums"][:5], st["loss_sums"][:5], rtol=2e-4)
 
 
-@pytest.mark.parametrize("algo", ["staged", "fused"])
+@pytest.mark.parametrize("algo", ["staged", "fused", "fused_ffma"])
 def test_shards_reproduce_the_full_batch(algo):
     """Batch sharding: running contiguous shards with b_global0 = first global sequence
     index reproduces the unsharded forward bit for bit (device RNG is keyed by the global index)."""

@@ -1,4 +1,4 @@
-"""tcgen05 building blocks (smct_tc.cuh): three-term bf16 split GEMM through TMEM vs an fp64 reference."""
+"""tcgen05 building blocks (smct_tc.cuh): three-term scaled-fp16 split GEMM through TMEM vs an fp64 reference."""
 import numpy as np
 import pytest
 import torch
@@ -20,4 +20,4 @@ def test_tc_selftest_matches_fp64(seed):
     ref = A.astype(np.float64) @ W.astype(np.float64)
     err = np.abs(D - ref).max()
     scale = np.abs(ref).max()
-    assert err <= 3e-5 * scale, (err, scale)
+    assert err <= 1e-6 * scale, (err, scale)   # fp16 x2 split with exact power-of-two scaling: ~22 mantissa bits

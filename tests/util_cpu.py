@@ -21,9 +21,11 @@ def make_case(cfg, seed=0, sigma2=0.5, multi=False, random_bias=True):
     return p, x_in, y, eps, u
 
 
-def screen_uniforms(cfg, p, x_in, y, eps, u, margin=1e-6, seed=5, max_iter=20):
+def screen_uniforms(cfg, p, x_in, y, eps, u, margin=1e-4, seed=5, max_iter=200):
     """Free-running parity protocol (L4): re-draw every uniform whose target sits within `margin`
-    (relative to the total mass) of a CDF boundary of the oracle's own trajectory."""
+    (relative to the total mass) of a CDF boundary of the oracle's own trajectory.  Log-weights of the CUDA
+    paths agree with the oracle to ~1e-6 (fp32 paths) / ~1e-5 (tensor-core path, bf16x3 operands), so a draw
+    that close to a boundary may legitimately land on the other side and fork the trajectory."""
     rng = np.random.default_rng(seed)
     u = u.copy()
     for _ in range(max_iter):
