@@ -347,23 +347,16 @@ int forward_fused(const smct_shape& s, const smct_params& pr, const smct_io& io,
 
   smct::MatArgs m;
   memset(&m, 0, sizeof(m));
-  m.B = B; m.P = P; m.S = S; m.Sa = Sa; m.Kp = Kp; m.Vp = Vp; m.Rp = Rp; m.A0 = A0; m.A1 = A1; m.pos = pos; m.aflag = aflag;
-  m.K = io.K; m.V = io.V; m.R = io.R;
-  smct::materialize_kernel<<<(unsigned)((long long)B * P), 256, 0, st>>>(m);
-  SMCT_LAUNCH_CHECK("materialize_kernel");
-
-  smct::FinalArgs f;
-  memset(&f, 0, sizeof(f));
-  f.B = B; f.P = P; f.S = S; f.D = D; f.Fy = s.F_y; f.weights_mode = s.weights_mode; f.logvar_dim = s.logvar_dim;
-  f.K = io.K; f.V = io.V; f.R = io.R;
+  m.B = B; m.P = P; m.S = S; m.Sa = Sa; m.Fy = s.F_y; m.logvar_dim = s.logvar_dim;
+  m.Kp = Kp; m.Vp = Vp; m.Rp = Rp; m.A0 = A0; m.A1 = A1; m.pos = pos; m.aflag = aflag;
   const bool want_noise = io.noise_K || io.noise_V || io.loss_sums;
-  f.kx = want_noise ? kx : nullptr; f.vx = want_noise ? vx : nullptr;
-  f.Wo = pr.Wo; f.logvar_k = pr.logvar_k; f.logvar_v = pr.logvar_v;
-  f.y = io.y;
-  f.pred_resampl = io.pred_resampl; f.noise_K = io.noise_K; f.noise_V = io.noise_V; f.loss_sums = io.loss_sums;
-  const long long nrows = (long long)B * P * S;
-  smct::final_kernel<<<(int)std::min<long long>((nrows + 7) / 8, 148LL * 32), 256, 0, st>>>(f);
-  SMCT_LAUNCH_CHECK("final_kernel");
+  m.kx = want_noise ? kx : nullptr; m.vx = want_noise ? vx : nullptr;
+  m.Wo = pr.Wo; m.logvar_k = pr.logvar_k; m.logvar_v = pr.logvar_v;
+  m.y = io.loss_sums ? (const float*)io.y : nullptr;
+  m.K = io.K; m.V = io.V; m.R = io.R;
+  m.pred_resampl = io.pred_resampl; m.noise_K = io.noise_K; m.noise_V = io.noise_V; m.loss_sums = io.loss_sums;
+  smct::materialize_final_kernel<<<(unsigned)((long long)B * P), 256, 0, st>>>(m);
+  SMCT_LAUNCH_CHECK("materialize_final_kernel");
   return SMCT_OK;
 }
 

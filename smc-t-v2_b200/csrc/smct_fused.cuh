@@ -518,30 +518,90 @@ __global__ void __launch_bounds__(FNT, 1) fused_forward_kernel(const FusedArgs a
 }
 
 // ------------------------------------------------------------------------------------------
-// materialize_kernel: K,V,R (B,P,S,64) <- slot-major physical rows through the final ancestry table
-// one CTA per (b, logical particle)
+// materialize_final_kernel: K,V,R (B,P,S,64) <- slot-major physical rows through the final ancestry table,
+// fused with the output heads of SMC_Transformer.call (SMC_Transformer.py:231-236): pred_resampl = R·Wo,
+// noise_K = K - wk(X), noise_V = V - wv(X) and the loss sums — one pass over the state instead of two.
+// One CTA per (b, logical particle); a half-warp (16 lanes x float4) owns one 64-float row.
 // ------------------------------------------------------------------------------------------
 struct MatArgs {
-  int B, P, S, Sa;
+  int B, P, S, Sa, Fy, logvar_dim;
   const float *Kp, *Vp, *Rp;
   const unsigned short *A0, *A1, *pos;
   const int* aflag;
+  const float *kx, *vx, *Wo, *logvar_k, *logvar_v;
+  const float* y;            // (B,S,Fy) or null
   float *K, *V, *R;
+  float *pred_resampl, *noise_K, *noise_V;
+  double* loss_sums;         // [0] K, [2] V, [4] sum (y - pred_resampl)^2
 };
 
-__global__ void __launch_bounds__(256) materialize_kernel(const MatArgs a) {
+__global__ void __launch_bounds__(256) materialize_final_kernel(const MatArgs a) {
+  __shared__ double red[3][8];
   const long long bp = blockIdx.x;
   const int b = (int)(bp / a.P);
   const int q = a.pos[bp];
   const unsigned short* Arow = (a.aflag[b] ? a.A0 : a.A1) + ((long long)b * a.P + q) * a.Sa;
-  const int c4 = threadIdx.x & 15;
-  for (int s = threadIdx.x >> 4; s < a.S; s += 16) {
+  const int tid = threadIdx.x, c4 = tid & 15, lane = tid & 31, wid = tid >> 5;
+  const unsigned hmask = (lane & 16) ? 0xFFFF0000u : 0x0000FFFFu;   // shuffles stay inside the half-warp
+  const int Fy = a.Fy;
+  float ivk[4], ivv[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int d = a.logvar_dim > 1 ? (4 * c4 + e) : 0;
+    ivk[e] = a.kx ? expf(-a.logvar_k[d]) : 0.f;
+    ivv[e] = a.kx ? expf(-a.logvar_v[d]) : 0.f;
+  }
+  float lk = 0.f, lv = 0.f, ly = 0.f;
+  for (int s = tid >> 4; s < a.S; s += 16) {
     const int row = Arow[s];
     const long long src = (((long long)b * a.S + s) * a.P + row) * FD + 4 * c4;
     const long long dst = (bp * a.S + s) * FD + 4 * c4;
-    *reinterpret_cast<float4*>(a.K + dst) = *reinterpret_cast<const float4*>(a.Kp + src);
-    *reinterpret_cast<float4*>(a.V + dst) = *reinterpret_cast<const float4*>(a.Vp + src);
-    *reinterpret_cast<float4*>(a.R + dst) = *reinterpret_cast<const float4*>(a.Rp + src);
+    const float4 k4 = *reinterpret_cast<const float4*>(a.Kp + src);
+    const float4 v4 = *reinterpret_cast<const float4*>(a.Vp + src);
+    const float4 r4 = *reinterpret_cast<const float4*>(a.Rp + src);
+    *reinterpret_cast<float4*>(a.K + dst) = k4;
+    *reinterpret_cast<float4*>(a.V + dst) = v4;
+    *reinterpret_cast<float4*>(a.R + dst) = r4;
+    if (a.kx) {
+      const long long xs = ((long long)b * a.S + s) * FD + 4 * c4;
+      const float4 kx4 = *reinterpret_cast<const float4*>(a.kx + xs);
+      const float4 vx4 = *reinterpret_cast<const float4*>(a.vx + xs);
+      const float4 nk = make_float4(k4.x - kx4.x, k4.y - kx4.y, k4.z - kx4.z, k4.w - kx4.w);
+      const float4 nv = make_float4(v4.x - vx4.x, v4.y - vx4.y, v4.z - vx4.z, v4.w - vx4.w);
+      if (a.noise_K) *reinterpret_cast<float4*>(a.noise_K + dst) = nk;
+      if (a.noise_V) *reinterpret_cast<float4*>(a.noise_V + dst) = nv;
+      lk = fmaf(nk.x * nk.x, ivk[0], fmaf(nk.y * nk.y, ivk[1], fmaf(nk.z * nk.z, ivk[2], fmaf(nk.w * nk.w, ivk[3], lk))));
+      lv = fmaf(nv.x * nv.x, ivv[0], fmaf(nv.y * nv.y, ivv[1], fmaf(nv.z * nv.z, ivv[2], fmaf(nv.w * nv.w, ivv[3], lv))));
+    }
+    if (a.pred_resampl || a.y) {
+      for (int f = 0; f < Fy; ++f) {
+        const float* w = a.Wo + (4 * c4) * Fy + f;
+        float part = fmaf(r4.x, __ldg(w), fmaf(r4.y, __ldg(w + Fy), fmaf(r4.z, __ldg(w + 2 * Fy), r4.w * __ldg(w + 3 * Fy))));
+        part += __shfl_xor_sync(hmask, part, 1);
+        part += __shfl_xor_sync(hmask, part, 2);
+        part += __shfl_xor_sync(hmask, part, 4);
+        part += __shfl_xor_sync(hmask, part, 8);
+        if (c4 == 0) {
+          if (a.pred_resampl) a.pred_resampl[(bp * a.S + s) * Fy + f] = part;
+          if (a.y) {
+            const float diff = a.y[((long long)b * a.S + s) * Fy + f] - part;
+            ly = fmaf(diff, diff, ly);
+          }
+        }
+      }
+    }
+  }
+  if (a.loss_sums) {
+    lk = warp_sum(lk); lv = warp_sum(lv); ly = warp_sum(ly);
+    if (lane == 0) { red[0][wid] = lk; red[1][wid] = lv; red[2][wid] = ly; }
+    __syncthreads();
+    if (tid == 0) {
+      double s0 = 0, s1 = 0, s2 = 0;
+      for (int i = 0; i < 8; ++i) { s0 += red[0][i]; s1 += red[1][i]; s2 += red[2][i]; }
+      atomicAdd(a.loss_sums + 0, s0);
+      atomicAdd(a.loss_sums + 2, s1);
+      atomicAdd(a.loss_sums + 4, s2);
+    }
   }
 }
 
