@@ -78,6 +78,19 @@ typedef struct smct_params {
   const float *logvar_k, *logvar_q, *logvar_v, *logvar_z; /* (logvar_dim) */
 } smct_params;
 
+/* Device pointers to gradient buffers, one per parameter (same names/shapes as smct_params; fp32).  smct_backward
+ * ACCUMULATES into them (zero them before the first shard/chunk of a step); NULL entries are skipped. */
+typedef struct smct_grads {
+  float *Wq, *bq, *Wk, *bk, *Wv, *bv, *Wz, *bz;
+  float *ln1_g, *ln1_b, *ln2_g, *ln2_b;
+  float *W1, *b1, *W2, *b2;
+  float *Wo;
+  float *W_in, *b_in;
+  float *logvar_k, *logvar_q, *logvar_v, *logvar_z;
+} smct_grads;
+
+enum { SMCT_LOSS_PYC = 0, SMCT_LOSS_CHECKOUT = 1 };
+
 /* Inputs / outputs of one forward pass.  Optional pointers may be NULL. */
 typedef struct smct_io {
   const void *x_in;        /* (B,S,F_x) f32 | (B,S) i32 tokens | (B,S,D) f32 encoded */
@@ -111,6 +124,24 @@ size_t smct_workspace_bytes(const smct_shape *shape);
  * (encode, zero state, S cell steps, output heads, resampled noises).                           */
 int smct_forward(const smct_shape *shape, const smct_params *params, const smct_io *io,
                  void *workspace, size_t workspace_bytes, void *stream);
+
+/* tape.gradient(loss, smc_transformer.trainable_variables) of train_step_SMC_T — src/train/train_step_functions.py:43-63
+ * for the regression loss of compute_SMC_loss (SMC_Transformer.py:123-146; regression-era form recovered from the pyc):
+ *   loss = inv_n * sum_{b,p,s} [ 1/2 sum_n ||noise_n||^2/sigma_n^2 + 1/2 ||y - pred_resampl||^2/Sigma_obs ]
+ *   (+ the log-determinant terms when loss_variant == SMCT_LOSS_CHECKOUT; they only touch the log-variances).
+ * Driven by the OUTPUTS of smct_forward on the same shape/params/inputs: io->K, io->V (final states), io->i_out
+ * (ancestor indices), io->loss_sums (for the log-variance gradients), io->x_in, io->y and the same io->eps or
+ * io->seed.  inv_n = 1 / (global B*P*S) so that chunks / shards of one optimisation step can be accumulated.
+ * Supported: gaussian weights, 1 head, full model, scalar log-variances, noise_z_mode = SMCT_NOISE_Z_PYC,
+ * d_model <= 128, S*d_model <= 12800.  Gradients are ACCUMULATED into `grads`. */
+size_t smct_backward_workspace_bytes(const smct_shape *shape);
+int smct_backward(const smct_shape *shape, const smct_params *params, const smct_io *io, const smct_grads *grads,
+                  float inv_n, int32_t loss_variant, void *workspace, size_t workspace_bytes, void *stream);
+
+/* optimizer.apply_gradients of tf.keras.optimizers.Adam (run_SMC_T.py:18-22): one parameter tensor of n elements.
+ * lr_t = lr * sqrt(1 - beta2^t) / (1 - beta1^t) is computed by the caller. */
+int smct_adam_step(int64_t n, float *param, const float *grad, float *m, float *v, float lr_t, float beta1,
+                   float beta2, float epsilon, void *stream);
 
 /* SMC_Transf_Cell.call(inputs, states) — src/models/SMC_Transformer/SMC_TransformerCell.py:129-184
  * One timestep t on explicit states.  x (B,P,D) encoded input of this step (x_per_particle=1) or

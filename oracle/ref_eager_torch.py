@@ -36,8 +36,7 @@ def _categorical(logits, u):
     return torch.searchsorted(cdf, tgt, right=True).clamp_(max=logits.shape[1] - 1)
 
 
-@torch.no_grad()
-def forward(cfg, p, x_in, y, eps=None, u=None, generator=None):
+def forward(cfg, p, x_in, y, eps=None, u=None, generator=None, i_forced=None):
     """cfg: oracle Config (gaussian weights, linear input).  p: dict of torch CPU fp32 tensors.
     x_in (B,S,F_x), y (B,S,F_y) torch CPU.  eps (4,S,B,P,D) / u (S,B,P) optional injected draws."""
     B, P, S, D, H = cfg.B, cfg.P, cfg.S, cfg.D, cfg.H
@@ -67,9 +66,9 @@ def forward(cfg, p, x_in, y, eps=None, u=None, generator=None):
         v_ = x @ p["Wv"] + p["bv"]
         ek, eq, ev, ez = ((eps[i, t].unsqueeze(2) if eps is not None else torch.randn(B, P, 1, D, generator=generator))
                           for i in range(4))
-        k = k_ + sk * ek
-        q = q_ + sq * eq
-        v = v_ + sv * ev
+        k = k_ + sk.detach() * ek      # stop_gradient on the noise scale (self_attention_SMC.py:98-104)
+        q = q_ + sq.detach() * eq
+        v = v_ + sv.detach() * ev
         noise_q = q - q_
         kh, qh, vh, Kh, Vh = split_heads(k), split_heads(q), split_heads(v), split_heads(K), split_heads(V)
         Kh = torch.cat([Kh[:, :, :, :t], kh, Kh[:, :, :, t + 1:]], dim=3)
@@ -87,7 +86,7 @@ def forward(cfg, p, x_in, y, eps=None, u=None, generator=None):
         K = concat_heads(Kh)
         V = concat_heads(Vh)
         z_proj = z_ @ p["Wz"] + p["bz"]
-        z = z_proj + sz * ez
+        z = z_proj + sz.detach() * ez
         noise_z = (z - z_) if cfg.noise_z_mode == "checkout" else (z - z_proj)
         if cfg.full_model:
             o = _ln(z + x, p["ln1_g"], p["ln1_b"], cfg.ln_eps)
@@ -100,8 +99,12 @@ def forward(cfg, p, x_in, y, eps=None, u=None, generator=None):
         diff = yt - pred
         logw = (-0.5 * (diff * diff).sum(-1).squeeze(-1)) / cfg.sigma_obs         # (B,P)
         logw = logw - torch.logsumexp(logw, dim=1, keepdim=True)
-        ut = u[t] if u is not None else torch.rand(B, P, dtype=torch.float64, generator=generator)
-        i_t = _categorical(logw, ut)
+        logw = logw.detach()                                                       # w, i_t are stop_gradient (:167)
+        if i_forced is not None:
+            i_t = i_forced[t].long()
+        else:
+            ut = u[t] if u is not None else torch.rand(B, P, dtype=torch.float64, generator=generator)
+            i_t = _categorical(logw, ut)
         if cfg.len_resampling is None or t < cfg.len_resampling:
             KVR = torch.cat([K, V, R], dim=-1)                                     # SMC_TransformerCell.py:170-172
             KVR = torch.gather(KVR, 1, i_t.reshape(B, P, 1, 1).expand(B, P, S, 3 * D))
@@ -120,6 +123,37 @@ def forward(cfg, p, x_in, y, eps=None, u=None, generator=None):
     return dict(pred=pred, pred_resampl=pred_resampl, K=K, V=V, R=R, w=torch.stack(w_list, dim=-1),
                 i_t=torch.stack(i_list), noise_q=torch.cat(nq_list, 2), noise_z=torch.cat(nz_list, 2),
                 noise_K_resampled=noise_K, noise_V_resampled=noise_V)
+
+
+def loss_and_grads(cfg, p_np, x_in, y, eps, i_forced, variant="pyc"):
+    """Gradient oracle: torch autograd through this restatement (fp64), with injected draws and
+    teacher-forced ancestor indices.  Returns (loss, {name: grad ndarray}).  The reference takes
+    tape.gradient(loss, trainable_variables) of exactly this graph (train_step_functions.py:43-63)."""
+    import numpy as np
+    tp = {k: torch.tensor(np.asarray(v, np.float64).reshape(()) if k.startswith("logvar") and np.size(v) == 1
+                          else np.asarray(v, np.float64), dtype=torch.float64, requires_grad=True) for k, v in p_np.items()}
+    old = torch.get_default_dtype()
+    torch.set_default_dtype(torch.float64)
+    try:
+        out = forward(cfg, tp, torch.as_tensor(np.asarray(x_in, np.float64)), torch.as_tensor(np.asarray(y, np.float64)),
+                      eps=torch.as_tensor(np.asarray(eps, np.float64)), i_forced=torch.as_tensor(np.asarray(i_forced)))
+        B, S = cfg.B, cfg.S
+        tot = 0.0
+        for n, lv in (("noise_K_resampled", "logvar_k"), ("noise_q", "logvar_q"), ("noise_V_resampled", "logvar_v"),
+                      ("noise_z", "logvar_z")):
+            part = 0.5 * (out[n].square() / torch.exp(tp[lv])).sum(-1)
+            if variant == "checkout":
+                D = out[n].shape[-1]
+                part = part + 0.5 * D * math.log(2 * math.pi) + 0.5 * D * tp[lv]
+            tot = tot + part.mean()
+        diff = torch.as_tensor(np.asarray(y, np.float64)).reshape(B, 1, S, cfg.F_y) - out["pred_resampl"]
+        loss = tot + (0.5 / cfg.sigma_obs) * diff.square().sum(-1).mean()
+        names = list(tp)
+        grads = torch.autograd.grad(loss, [tp[n] for n in names], allow_unused=True)
+    finally:
+        torch.set_default_dtype(old)
+    return float(loss), {n: (np.zeros_like(np.asarray(p_np[n], np.float64)) if g is None else g.detach().numpy().reshape(np.shape(p_np[n])))
+                         for n, g in zip(names, grads)}
 
 
 def loss_pyc(cfg, p, out, y):

@@ -32,6 +32,16 @@ class SmctParams(ctypes.Structure):
     _fields_ = [(n, VP) for n in PARAM_FIELDS]
 
 
+GRAD_FIELDS = PARAM_FIELDS
+
+
+class SmctGrads(ctypes.Structure):
+    _fields_ = [(n, VP) for n in GRAD_FIELDS]
+
+
+LOSS = {"pyc": 0, "checkout": 1}
+
+
 class SmctIO(ctypes.Structure):
     _fields_ = [("x_in", VP), ("y", VP), ("eps", VP), ("u", VP), ("i_forced", VP), ("seed", ctypes.c_uint64),
                 ("pred", VP), ("pred_resampl", VP), ("K", VP), ("V", VP), ("R", VP), ("w", VP), ("i_out", VP),
@@ -51,6 +61,7 @@ _lib = None
 def _declare(lib):
     i32, i64, u64, f32 = ctypes.c_int32, ctypes.c_int64, ctypes.c_uint64, ctypes.c_float
     SP, PP, IP = ctypes.POINTER(SmctShape), ctypes.POINTER(SmctParams), ctypes.POINTER(SmctIO)
+    GP = ctypes.POINTER(SmctGrads)
     sig = {
         "smct_abi_version": (ctypes.c_int, []),
         "smct_last_error": (ctypes.c_char_p, []),
@@ -58,6 +69,9 @@ def _declare(lib):
         "smct_launch_count": (ctypes.c_longlong, [ctypes.c_int]),
         "smct_workspace_bytes": (ctypes.c_size_t, [SP]),
         "smct_forward": (ctypes.c_int, [SP, PP, IP, VP, ctypes.c_size_t, VP]),
+        "smct_backward_workspace_bytes": (ctypes.c_size_t, [SP]),
+        "smct_backward": (ctypes.c_int, [SP, PP, IP, GP, f32, i32, VP, ctypes.c_size_t, VP]),
+        "smct_adam_step": (ctypes.c_int, [i64, VP, VP, VP, VP, f32, f32, f32, f32, VP]),
         "smct_cell_step": (ctypes.c_int, [SP, PP, i32, VP, i32, VP, VP, VP, VP, u64, VP, VP, VP, VP, VP, VP, VP, VP,
                                           VP, VP, VP, ctypes.c_size_t, VP]),
         "smct_attention_step": (ctypes.c_int, [SP, PP, i32, VP, VP, u64, VP, VP, VP, VP, VP, VP, VP, VP, VP,

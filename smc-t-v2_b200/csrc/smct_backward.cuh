@@ -1,0 +1,548 @@
+// smct_backward.cuh — backward pass of the SMC-Transformer forward.
+//
+// tape.gradient(loss, trainable_variables) of train_step_SMC_T (src/train/train_step_functions.py:43-63) for
+// the regression loss: loss = mean_{b,p,s} [ 1/2 sum_n ||noise_n||^2/sigma_n^2 + 1/2 ||y - pred_resampl||^2/Sigma_obs ].
+//
+// Path-wise formulation.  Weights and ancestor indices are stop_gradient (SMC_TransformerCell.py:167), the
+// noise scale is stop_gradient (self_attention_SMC.py:98-104), and the loss only sees the FINAL resampled
+// states.  The final state of particle p, K[b,p,0..S-1], V[..], R[..], is exactly the lineage of p, so the
+// loss is a sum over B*P independent "paths": each path is one causal-attention + LN/FFN/LN + linear-head
+// sequence of length S whose inputs (x rows, noise constants) are known.  The backward is therefore driven
+// entirely by the forward's OUTPUTS (K, V final; ancestor indices; the RNG seed or injected eps) and needs no
+// genealogy bookkeeping: rows shared by several final particles are simply processed once per path.
+//   noise constants:  k_s - k_(x_s) and v_s - v_(x_s) are recovered from the stored rows;
+//                     eps_q / eps_z of row (path p, slot s) belong to the logical particle anc[b,p,s] that p
+//                     descends from at time s (traced from i_out) and are regenerated (Philox) or read (eps).
+// Kernels (correctness-first, generic d_model <= 128, 1 head, full model):
+//   anc_trace_kernel        lineage of every final particle in logical ids
+//   bwd_attn_fwd_kernel     recompute q, attention output z_ and the softmax statistics per row
+//   bwd_dense_kernel        per 32-particle tile at one (b,s): recompute dense forward, back-propagate to dz_,
+//                           weight gradients into CTA-private replicas (no float atomics on weights)
+//   bwd_attn_bwd_kernel     per group of paths: dq, dk, dv (+ the direct K/V noise terms), reduced over particles
+//   bwd_rows_kernel         shared rows (b,s): Q/K/V projections, LN1(x), input encoding
+//   reduce_replicas_kernel  sum of the replicas into the gradient buffers
+#pragma once
+#include "smct_common.cuh"
+#include "smct_staged.cuh"
+#include "../../include/smct.h"
+
+namespace smct {
+
+// offsets (in floats) of every parameter inside one gradient replica
+struct GradLayout {
+  int Wq, bq, Wk, bk, Wv, bv, Wz, bz, ln1_g, ln1_b, ln2_g, ln2_b, W1, b1, W2, b2, Wo, W_in, b_in, total;
+};
+
+struct BwdArgs {
+  int B, P, S, D, dff, Fy, Fx, attn_window, len_resampling, input_mode;
+  float ln_eps, sigma_obs, inv_n, sqrtD;
+  long long b_global0;
+  unsigned long long seed;
+  const void* x_in;
+  const float *X, *xln, *q_, *kx, *vx;   // (B,S,D) rows (rows_kernel)
+  const float* y;                         // (B,S,Fy)
+  const float* eps;                       // optional (4,S,B,P,D)
+  smct_params p;
+  const float *WzT, *W1T, *W2T;           // transposed weights
+  const float *K, *V;                     // (B,P,S,D) final states
+  const int* i_out;                       // (S,B,P)
+  unsigned short* anc;                    // (B,P,S)
+  float *Zm, *dZm, *stat;                 // (B,P,S,D), (B,P,S,D), (B,P,S,2)
+  float *dq_sum, *dk_sum, *dv_sum, *dxln_sum, *dkx_sum, *dvx_sum;   // (B,S,D)
+  float* rep;                             // nrep x layout.total gradient replicas
+  int nrep;
+  GradLayout lay;
+};
+
+__global__ void anc_trace_kernel(int B, int P, int S, int len_resampling, const int* i_out, unsigned short* anc) {
+  const long long n = (long long)B * P;
+  for (long long bp = (long long)blockIdx.x * blockDim.x + threadIdx.x; bp < n; bp += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(bp / P);
+    int l = (int)(bp % P);
+    for (int t = S - 1; t >= 0; --t) {
+      if (len_resampling < 0 || t < len_resampling) l = i_out[((long long)t * B + b) * P + l];
+      anc[bp * S + t] = (unsigned short)l;
+    }
+  }
+}
+
+__global__ void transpose_kernel(const float* in, float* out, int rows, int cols) {   // out[c][r] = in[r][c]
+  const long long n = (long long)rows * cols;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / cols), c = (int)(i % cols);
+    out[(long long)c * rows + r] = in[i];
+  }
+}
+
+__device__ __forceinline__ float bwd_eps(const BwdArgs& a, int which, int b, int s, int L, int d) {
+  if (a.eps) return a.eps[((((long long)which * a.S + s) * a.B + b) * a.P + L) * a.D + d];
+  const unsigned long long gbp = (unsigned long long)(a.b_global0 + b) * (unsigned long long)a.P + L;
+  return philox_normal1(a.seed, (uint32_t)which, (uint32_t)s, gbp, (a.D + 3) >> 2, d);
+}
+
+// ------------------------------------------------------------------------------------------
+// attention forward recompute: one warp per row (b,p,s)
+// ------------------------------------------------------------------------------------------
+template <int KD>
+__global__ void __launch_bounds__(256) bwd_attn_fwd_kernel(const BwdArgs a) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int D = a.D, S = a.S;
+  const long long nrows = (long long)a.B * a.P * S;
+  const float std_q = expf(0.5f * a.p.logvar_q[0]);
+  const float sqrt_d = sqrtf((float)D);
+  for (long long row = (long long)blockIdx.x * 8 + wid; row < nrows; row += (long long)gridDim.x * 8) {
+    const int s = (int)(row % S);
+    const long long bp = row / S;
+    const int b = (int)(bp / a.P);
+    const int L = a.anc[row];
+    const int s_lo = (a.attn_window >= 0 && s > a.attn_window) ? s - a.attn_window : 0;
+    float q[KD], acc[KD];
+#pragma unroll
+    for (int k = 0; k < KD; ++k) {
+      const int d = lane + 32 * k;
+      q[k] = (d < D) ? __fadd_rn(a.q_[((long long)b * S + s) * D + d], __fmul_rn(std_q, bwd_eps(a, 1, b, s, L, d))) : 0.f;
+      acc[k] = 0.f;
+    }
+    const float* Kp = a.K + bp * S * D;
+    const float* Vp = a.V + bp * S * D;
+    float m = -INFINITY, l = 0.f;
+    for (int t = s_lo; t <= s; ++t) {
+      float part = 0.f, vr[KD];
+#pragma unroll
+      for (int k = 0; k < KD; ++k) {
+        const int d = lane + 32 * k;
+        const float kv = (d < D) ? Kp[(long long)t * D + d] : 0.f;
+        vr[k] = (d < D) ? Vp[(long long)t * D + d] : 0.f;
+        part = fmaf(q[k], kv, part);
+      }
+      const float sc = warp_sum(part) / sqrt_d;
+      const float mn = fmaxf(m, sc);
+      const float corr = expf(m - mn), pj = expf(sc - mn);
+      l = l * corr + pj;
+#pragma unroll
+      for (int k = 0; k < KD; ++k) acc[k] = fmaf(pj, vr[k], acc[k] * corr);
+      m = mn;
+    }
+#pragma unroll
+    for (int k = 0; k < KD; ++k) {
+      const int d = lane + 32 * k;
+      if (d < D) a.Zm[row * D + d] = acc[k] / l;
+    }
+    if (lane == 0) { a.stat[row * 2] = m; a.stat[row * 2 + 1] = l; }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// dense forward recompute + backward: persistent CTAs, one tile = 32 particles at one (b,s)
+// ------------------------------------------------------------------------------------------
+// rep[(k,n)] += sum_rows A[row][k] * Bm[row][n]   (CTA-private replica: plain read-modify-write)
+__device__ __forceinline__ void tile_outer_accum(const float* A, int lda, const float* Bm, int ldb, int Kdim, int N, float* rep) {
+  for (int idx = threadIdx.x; idx < Kdim * N; idx += NT) {
+    const int k = idx / N, n = idx - k * N;
+    float acc = 0.f;
+#pragma unroll 8
+    for (int r = 0; r < PT; ++r) acc = fmaf(A[r * lda + k], Bm[r * ldb + n], acc);
+    rep[idx] += acc;
+  }
+}
+
+template <int KD>
+__global__ void __launch_bounds__(NT) bwd_dense_kernel(const BwdArgs a) {
+  extern __shared__ float sm[];
+  const int D = a.D, Dp = D + 1, dff = a.dff, Fp = dff + 1, S = a.S, P = a.P, Fy = a.Fy;
+  float* Zt = sm;                 // z_ tile
+  float* Ut = Zt + PT * Dp;       // normalised LN1 input (u hat)
+  float* Ot = Ut + PT * Dp;       // o = LN1(z + x)
+  float* Gt = Ot + PT * Dp;       // g = ffn + o, then dg
+  float* dOt = Gt + PT * Dp;      // do, then du
+  float* Ht = dOt + PT * Dp;      // h = relu(o W1 + b1)
+  float* dHt = Ht + PT * Fp;      // d hpre
+  float* rstd1 = dHt + PT * Fp;   // PT
+  float* g_small = rstd1 + PT;    // bz, ln1_g, ln1_b, ln2_g, ln2_b, b2 (6*D), b1 (dff), Wo (D*Fy), dxs (D)
+  float* g_bz = g_small; float* g_l1g = g_bz + D; float* g_l1b = g_l1g + D; float* g_l2g = g_l1b + D;
+  float* g_l2b = g_l2g + D; float* g_b2 = g_l2b + D; float* g_b1 = g_b2 + D; float* g_Wo = g_b1 + dff;
+  float* dxs = g_Wo + D * Fy;
+  const int n_small = 6 * D + dff + D * Fy;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  float* rep = a.rep + (long long)blockIdx.x * a.lay.total;
+  const float std_z = expf(0.5f * a.p.logvar_z[0]);
+  const float c_obs = a.inv_n / a.sigma_obs;
+  for (int i = tid; i < n_small; i += NT) g_small[i] = 0.f;
+  const int ptiles = (P + PT - 1) / PT;
+  const long long ntiles = (long long)a.B * S * ptiles;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int pt = (int)(tile % ptiles);
+    const long long bs = tile / ptiles;
+    const int s = (int)(bs % S), b = (int)(bs / S);
+    const int p0 = pt * PT, np = min(PT, P - p0);
+    const float* xrow = a.xln + bs * D;
+    __syncthreads();
+    // S1: z_ tile
+    for (int i = tid; i < PT * D; i += NT) {
+      const int pl = i / D, d = i - pl * D;
+      Zt[pl * Dp + d] = (pl < np) ? a.Zm[(((long long)b * P + p0 + pl) * S + s) * D + d] : 0.f;
+    }
+    for (int i = tid; i < D; i += NT) dxs[i] = 0.f;
+    __syncthreads();
+    // S2: u = dense(z_) + noise_z + x
+    tile_gemm(Zt, Dp, a.p.Wz, a.p.bz, D, D, [&](int pl, int n, float v) {
+      float u = 0.f;
+      if (pl < np) {
+        const int L = a.anc[(((long long)b * P + p0 + pl) * S) + s];
+        const float z = __fadd_rn(v, __fmul_rn(std_z, bwd_eps(a, 3, b, s, L, n)));
+        u = z + xrow[n];
+      }
+      Ut[pl * Dp + n] = u;
+    });
+    __syncthreads();
+    // S3: LN1
+    for (int pl = wid; pl < PT; pl += NW) {
+      float v[KD], s1 = 0.f;
+#pragma unroll
+      for (int k = 0; k < KD; ++k) { const int d = lane + 32 * k; v[k] = (d < D) ? Ut[pl * Dp + d] : 0.f; s1 += v[k]; }
+      const float mean = warp_sum(s1) / (float)D;
+      float s2 = 0.f;
+#pragma unroll
+      for (int k = 0; k < KD; ++k) { const int d = lane + 32 * k; const float c = (d < D) ? v[k] - mean : 0.f; s2 = fmaf(c, c, s2); }
+      const float rstd = 1.0f / sqrtf(warp_sum(s2) / (float)D + a.ln_eps);
+      if (lane == 0) rstd1[pl] = rstd;
+#pragma unroll
+      for (int k = 0; k < KD; ++k) {
+        const int d = lane + 32 * k;
+        if (d < D) {
+          const float uh = (v[k] - mean) * rstd;
+          Ut[pl * Dp + d] = uh;
+          Ot[pl * Dp + d] = uh * a.p.ln1_g[d] + a.p.ln1_b[d];
+        }
+      }
+    }
+    __syncthreads();
+    // S4, S5: FFN forward
+    tile_gemm(Ot, Dp, a.p.W1, a.p.b1, D, dff, [&](int pl, int j, float v) { Ht[pl * Fp + j] = fmaxf(v, 0.f); });
+    __syncthreads();
+    tile_gemm(Ht, Fp, a.p.W2, a.p.b2, dff, D, [&](int pl, int n, float v) { Gt[pl * Dp + n] = v + Ot[pl * Dp + n]; });
+    __syncthreads();
+    // S6: LN2, output head, loss gradient, LN2 backward
+    for (int pl = wid; pl < PT; pl += NW) {
+      float gh[KD], r[KD], s1 = 0.f;
+#pragma unroll
+      for (int k = 0; k < KD; ++k) { const int d = lane + 32 * k; gh[k] = (d < D) ? Gt[pl * Dp + d] : 0.f; s1 += gh[k]; }
+      const float mean = warp_sum(s1) / (float)D;
+      float s2 = 0.f;
+#pragma unroll
+      for (int k = 0; k < KD; ++k) { const int d = lane + 32 * k; const float c = (d < D) ? gh[k] - mean : 0.f; s2 = fmaf(c, c, s2); }
+      const float rstd = 1.0f / sqrtf(warp_sum(s2) / (float)D + a.ln_eps);
+      float dr[KD];
+#pragma unroll
+      for (int k = 0; k < KD; ++k) {
+        const int d = lane + 32 * k;
+        gh[k] = (d < D) ? (gh[k] - mean) * rstd : 0.f;
+        r[k] = (d < D) ? gh[k] * a.p.ln2_g[d] + a.p.ln2_b[d] : 0.f;
+        dr[k] = 0.f;
+      }
+      if (pl < np) {
+        for (int f = 0; f < Fy; ++f) {
+          float part = 0.f;
+#pragma unroll
+          for (int k = 0; k < KD; ++k) { const int d = lane + 32 * k; if (d < D) part = fmaf(r[k], __ldg(a.p.Wo + (long long)d * Fy + f), part); }
+          const float pr = warp_sum(part);
+          const float dpred = (pr - a.y[bs * Fy + f]) * c_obs;
+#pragma unroll
+          for (int k = 0; k < KD; ++k) {
+            const int d = lane + 32 * k;
+            if (d < D) { dr[k] = fmaf(dpred, __ldg(a.p.Wo + (long long)d * Fy + f), dr[k]); atomicAdd(&g_Wo[d * Fy + f], r[k] * dpred); }
+          }
+        }
+      }
+      float t1 = 0.f, t2 = 0.f, dgh[KD];
+#pragma unroll
+      for (int k = 0; k < KD; ++k) {
+        const int d = lane + 32 * k;
+        dgh[k] = (d < D) ? dr[k] * a.p.ln2_g[d] : 0.f;
+        t1 += dgh[k]; t2 = fmaf(dgh[k], gh[k], t2);
+      }
+      const float m1 = warp_sum(t1) / (float)D, m2 = warp_sum(t2) / (float)D;
+#pragma unroll
+      for (int k = 0; k < KD; ++k) {
+        const int d = lane + 32 * k;
+        if (d < D) {
+          const float dg = rstd * (dgh[k] - m1 - gh[k] * m2);
+          Gt[pl * Dp + d] = dg;
+          if (pl < np) { atomicAdd(&g_l2g[d], dr[k] * gh[k]); atomicAdd(&g_l2b[d], dr[k]); atomicAdd(&g_b2[d], dg); }
+        }
+      }
+    }
+    __syncthreads();
+    // S7: d hpre = (dg W2^T) * relu'
+    tile_gemm(Gt, Dp, a.W2T, nullptr, D, dff, [&](int pl, int j, float v) { dHt[pl * Fp + j] = (Ht[pl * Fp + j] > 0.f) ? v : 0.f; });
+    // S8: dW2 += h^T dg      (reads Ht, Gt only: no hazard with S7's writes to dHt)
+    tile_outer_accum(Ht, Fp, Gt, Dp, dff, D, rep + a.lay.W2);
+    __syncthreads();
+    // S9: do = d hpre W1^T + dg ; db1
+    tile_gemm(dHt, Fp, a.W1T, nullptr, dff, D, [&](int pl, int n, float v) { dOt[pl * Dp + n] = v + Gt[pl * Dp + n]; });
+    for (int j = tid; j < dff; j += NT) {
+      float acc = 0.f;
+      for (int r = 0; r < PT; ++r) acc += dHt[r * Fp + j];
+      g_b1[j] += acc;
+    }
+    // S10: dW1 += o^T d hpre
+    tile_outer_accum(Ot, Dp, dHt, Fp, D, dff, rep + a.lay.W1);
+    __syncthreads();
+    // S11: LN1 backward -> du (in dOt), dgamma1/dbeta1, sum over particles of du
+    for (int pl = wid; pl < PT; pl += NW) {
+      float dov[KD], uh[KD], duh[KD], t1 = 0.f, t2 = 0.f;
+#pragma unroll
+      for (int k = 0; k < KD; ++k) {
+        const int d = lane + 32 * k;
+        dov[k] = (d < D) ? dOt[pl * Dp + d] : 0.f;
+        uh[k] = (d < D) ? Ut[pl * Dp + d] : 0.f;
+        duh[k] = (d < D) ? dov[k] * a.p.ln1_g[d] : 0.f;
+        t1 += duh[k]; t2 = fmaf(duh[k], uh[k], t2);
+      }
+      const float m1 = warp_sum(t1) / (float)D, m2 = warp_sum(t2) / (float)D;
+      const float rstd = rstd1[pl];
+#pragma unroll
+      for (int k = 0; k < KD; ++k) {
+        const int d = lane + 32 * k;
+        if (d < D) {
+          const float du = (pl < np) ? rstd * (duh[k] - m1 - uh[k] * m2) : 0.f;
+          dOt[pl * Dp + d] = du;
+          if (pl < np) { atomicAdd(&g_l1g[d], dov[k] * uh[k]); atomicAdd(&g_l1b[d], dov[k]); atomicAdd(&dxs[d], du); }
+        }
+      }
+    }
+    __syncthreads();
+    // S12: dbz, d xln (sum over the tile's particles), dWz ; S13: dz_ = du Wz^T
+    for (int d = tid; d < D; d += NT) { g_bz[d] += dxs[d]; atomicAdd(a.dxln_sum + bs * D + d, dxs[d]); }
+    tile_outer_accum(Zt, Dp, dOt, Dp, D, D, rep + a.lay.Wz);
+    tile_gemm(dOt, Dp, a.WzT, nullptr, D, D, [&](int pl, int n, float v) {
+      if (pl < np) a.dZm[(((long long)b * P + p0 + pl) * S + s) * D + n] = v;
+    });
+  }
+  __syncthreads();
+  for (int i = tid; i < D; i += NT) {
+    rep[a.lay.bz + i] += g_bz[i]; rep[a.lay.ln1_g + i] += g_l1g[i]; rep[a.lay.ln1_b + i] += g_l1b[i];
+    rep[a.lay.ln2_g + i] += g_l2g[i]; rep[a.lay.ln2_b + i] += g_l2b[i]; rep[a.lay.b2 + i] += g_b2[i];
+  }
+  for (int i = tid; i < dff; i += NT) rep[a.lay.b1 + i] += g_b1[i];
+  for (int i = tid; i < D * Fy; i += NT) rep[a.lay.Wo + i] += g_Wo[i];
+}
+
+// ------------------------------------------------------------------------------------------
+// attention backward: one CTA per (b, group of PPC paths); warp per row; dk/dv summed over the group in smem
+// ------------------------------------------------------------------------------------------
+constexpr int BWD_PPC = 16;
+
+template <int KD>
+__global__ void __launch_bounds__(256) bwd_attn_bwd_kernel(const BwdArgs a) {
+  extern __shared__ float sm[];
+  const int D = a.D, S = a.S, P = a.P;
+  float* dKs = sm;                 // S*D: sum over the group's paths of dL/dk_tau (attention + direct noise term)
+  float* dVs = dKs + S * D;
+  float* dKX = dVs + S * D;        // direct terms only, with the sign of d/d kx
+  float* dVX = dKX + S * D;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int groups = (P + BWD_PPC - 1) / BWD_PPC;
+  const int b = blockIdx.x / groups, g = blockIdx.x % groups;
+  const int p0 = g * BWD_PPC, np = min(BWD_PPC, P - p0);
+  const float std_q = expf(0.5f * a.p.logvar_q[0]);
+  const float sqrt_d = sqrtf((float)D);
+  const float c_k = expf(-a.p.logvar_k[0]) * a.inv_n, c_v = expf(-a.p.logvar_v[0]) * a.inv_n;
+  for (int i = tid; i < 4 * S * D; i += 256) sm[i] = 0.f;
+  __syncthreads();
+  for (int pi = 0; pi < np; ++pi) {
+    const long long bp = (long long)b * P + p0 + pi;
+    const float* Kp = a.K + bp * S * D;
+    const float* Vp = a.V + bp * S * D;
+    for (int s = wid; s < S; s += 8) {
+      const long long row = bp * S + s;
+      const int L = a.anc[row];
+      const int s_lo = (a.attn_window >= 0 && s > a.attn_window) ? s - a.attn_window : 0;
+      float q[KD], dz[KD], dq[KD], part0 = 0.f;
+#pragma unroll
+      for (int k = 0; k < KD; ++k) {
+        const int d = lane + 32 * k;
+        const bool ok = d < D;
+        q[k] = ok ? __fadd_rn(a.q_[((long long)b * S + s) * D + d], __fmul_rn(std_q, bwd_eps(a, 1, b, s, L, d))) : 0.f;
+        dz[k] = ok ? a.dZm[row * D + d] : 0.f;
+        const float zz = ok ? a.Zm[row * D + d] : 0.f;
+        part0 = fmaf(dz[k], zz, part0);
+        dq[k] = 0.f;
+      }
+      const float delta = warp_sum(part0);     // sum_tau a_tau (dz . v_tau) = dz . z_
+      const float m = a.stat[row * 2], l = a.stat[row * 2 + 1];
+      for (int t = s_lo; t <= s; ++t) {
+        float pk = 0.f, pv = 0.f, kr[KD], vr[KD];
+#pragma unroll
+        for (int k = 0; k < KD; ++k) {
+          const int d = lane + 32 * k;
+          kr[k] = (d < D) ? Kp[(long long)t * D + d] : 0.f;
+          vr[k] = (d < D) ? Vp[(long long)t * D + d] : 0.f;
+          pk = fmaf(q[k], kr[k], pk);
+          pv = fmaf(dz[k], vr[k], pv);
+        }
+        const float sc = warp_sum(pk) / sqrt_d;
+        const float dA = warp_sum(pv);
+        const float at = expf(sc - m) / l;
+        const float dS = at * (dA - delta) / sqrt_d;
+#pragma unroll
+        for (int k = 0; k < KD; ++k) {
+          const int d = lane + 32 * k;
+          if (d < D) {
+            dq[k] = fmaf(dS, kr[k], dq[k]);
+            atomicAdd(&dKs[t * D + d], dS * q[k]);
+            atomicAdd(&dVs[t * D + d], at * dz[k]);
+          }
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < KD; ++k) {
+        const int d = lane + 32 * k;
+        if (d < D) atomicAdd(a.dq_sum + ((long long)b * S + s) * D + d, dq[k]);
+      }
+    }
+    // direct terms of the loss on the resampled K/V noises: 1/2 ||K - kx||^2 / sigma_k^2 (same for V)
+    for (int i = tid; i < S * D; i += 256) {
+      const float tk = c_k * (Kp[i] - a.kx[(long long)b * S * D + i]);
+      const float tv = c_v * (Vp[i] - a.vx[(long long)b * S * D + i]);
+      atomicAdd(&dKs[i], tk); atomicAdd(&dVs[i], tv);
+      atomicAdd(&dKX[i], -tk); atomicAdd(&dVX[i], -tv);
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < S * D; i += 256) {
+    const long long o = (long long)b * S * D + i;
+    atomicAdd(a.dk_sum + o, dKs[i]); atomicAdd(a.dv_sum + o, dVs[i]);
+    atomicAdd(a.dkx_sum + o, dKX[i]); atomicAdd(a.dvx_sum + o, dVX[i]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// shared rows (b,s): q_/k_/v_ projections of LN1(X), kx/vx projections of X, LN1 backward, input encoding
+// persistent CTAs of 128 threads, CTA-private replica
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) bwd_rows_kernel(const BwdArgs a) {
+  extern __shared__ float sm[];
+  const int D = a.D, S = a.S;
+  float* Xs = sm;          // raw encoded row
+  float* xh = Xs + D;      // normalised
+  float* xl = xh + D;      // LN1(X)
+  float* dq = xl + D; float* dk = dq + D; float* dv = dk + D; float* dkx = dv + D; float* dvx = dkx + D;
+  float* t1 = dvx + D;     // d xln total
+  float* dX = t1 + D;
+  float* scratch = dX + D; // 32
+  const int tid = threadIdx.x;
+  float* rep = a.rep + (long long)blockIdx.x * a.lay.total;
+  const long long nrows = (long long)a.B * S;
+  for (long long row = blockIdx.x; row < nrows; row += gridDim.x) {
+    __syncthreads();
+    float s1 = 0.f;
+    for (int d = tid; d < D; d += 128) {
+      Xs[d] = a.X[row * D + d];
+      dq[d] = a.dq_sum[row * D + d]; dk[d] = a.dk_sum[row * D + d]; dv[d] = a.dv_sum[row * D + d];
+      dkx[d] = a.dkx_sum[row * D + d]; dvx[d] = a.dvx_sum[row * D + d];
+      s1 += Xs[d];
+    }
+    const float mean = block_sum(s1, scratch) / (float)D;
+    float s2 = 0.f;
+    for (int d = tid; d < D; d += 128) { const float c = Xs[d] - mean; s2 = fmaf(c, c, s2); }
+    const float rstd = 1.0f / sqrtf(block_sum(s2, scratch) / (float)D + a.ln_eps);
+    for (int d = tid; d < D; d += 128) {
+      xh[d] = (Xs[d] - mean) * rstd;
+      xl[d] = xh[d] * a.p.ln1_g[d] + a.p.ln1_b[d];
+    }
+    __syncthreads();
+    // d xln = (from the residual z + x) + dq Wq^T + dk Wk^T + dv Wv^T
+    float u1 = 0.f, u2 = 0.f;
+    for (int d = tid; d < D; d += 128) {
+      float acc = a.dxln_sum[row * D + d];
+      for (int n = 0; n < D; ++n)
+        acc = fmaf(dq[n], a.p.Wq[d * D + n], fmaf(dk[n], a.p.Wk[d * D + n], fmaf(dv[n], a.p.Wv[d * D + n], acc)));
+      t1[d] = acc;
+      const float dxh = acc * a.p.ln1_g[d];
+      u1 += dxh; u2 = fmaf(dxh, xh[d], u2);
+    }
+    const float m1 = block_sum(u1, scratch) / (float)D;
+    const float m2 = block_sum(u2, scratch) / (float)D;
+    for (int d = tid; d < D; d += 128) {
+      float acc = rstd * (t1[d] * a.p.ln1_g[d] - m1 - xh[d] * m2);
+      for (int n = 0; n < D; ++n) acc = fmaf(dkx[n], a.p.Wk[d * D + n], fmaf(dvx[n], a.p.Wv[d * D + n], acc));
+      dX[d] = acc;
+      rep[a.lay.ln1_g + d] += t1[d] * xh[d];
+      rep[a.lay.ln1_b + d] += t1[d];
+      rep[a.lay.bq + d] += dq[d];
+      rep[a.lay.bk + d] += dk[d] + dkx[d];
+      rep[a.lay.bv + d] += dv[d] + dvx[d];
+    }
+    __syncthreads();
+    for (int idx = tid; idx < D * D; idx += 128) {
+      const int k = idx / D, n = idx - k * D;
+      rep[a.lay.Wq + idx] += xl[k] * dq[n];
+      rep[a.lay.Wk + idx] += fmaf(xl[k], dk[n], Xs[k] * dkx[n]);
+      rep[a.lay.Wv + idx] += fmaf(xl[k], dv[n], Xs[k] * dvx[n]);
+    }
+    // input encoding: X = (x W_in + b_in) * sqrt(D)  |  X = emb[tok] * sqrt(D)
+    if (a.input_mode == SMCT_INPUT_LINEAR) {
+      const float* xr = (const float*)a.x_in + row * a.Fx;
+      for (int idx = tid; idx < a.Fx * D; idx += 128) {
+        const int f = idx / D, d = idx - f * D;
+        rep[a.lay.W_in + idx] += xr[f] * dX[d] * a.sqrtD;
+      }
+      for (int d = tid; d < D; d += 128) rep[a.lay.b_in + d] += dX[d] * a.sqrtD;
+    } else if (a.input_mode == SMCT_INPUT_EMBEDDING) {
+      const int tok = ((const int*)a.x_in)[row];
+      for (int d = tid; d < D; d += 128) rep[a.lay.W_in + (long long)tok * D + d] += dX[d] * a.sqrtD;
+    }
+  }
+}
+
+__global__ void reduce_replicas_kernel(const float* rep, int nrep, int total, float* out) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    float acc = 0.f;
+    for (int r = 0; r < nrep; ++r) acc += rep[(long long)r * total + i];
+    out[i] += acc;
+  }
+}
+
+// scatter the flat reduced gradient into the caller's per-parameter buffers (accumulating) + log-variance grads
+struct ScatterArgs {
+  GradLayout lay;
+  int D, dff, Fy, win_elems;
+  const float* flat;
+  const double* loss_sums;   // forward's sums: [0] K, [1] q, [2] V, [3] z
+  float inv_n, logdet_term;  // logdet_term = 0.5 * D * (rows of this call) * inv_n for the checkout loss variant, else 0
+  smct_grads g;
+};
+
+__global__ void scatter_grads_kernel(const ScatterArgs a) {
+  const int D = a.D, dff = a.dff;
+  const int i0 = blockIdx.x * blockDim.x + threadIdx.x, st = gridDim.x * blockDim.x;
+  auto put = [&](float* dst, int off, int n) {
+    if (!dst) return;
+    for (int i = i0; i < n; i += st) dst[i] += a.flat[off + i];
+  };
+  put(a.g.Wq, a.lay.Wq, D * D); put(a.g.bq, a.lay.bq, D); put(a.g.Wk, a.lay.Wk, D * D); put(a.g.bk, a.lay.bk, D);
+  put(a.g.Wv, a.lay.Wv, D * D); put(a.g.bv, a.lay.bv, D); put(a.g.Wz, a.lay.Wz, D * D); put(a.g.bz, a.lay.bz, D);
+  put(a.g.ln1_g, a.lay.ln1_g, D); put(a.g.ln1_b, a.lay.ln1_b, D); put(a.g.ln2_g, a.lay.ln2_g, D); put(a.g.ln2_b, a.lay.ln2_b, D);
+  put(a.g.W1, a.lay.W1, D * dff); put(a.g.b1, a.lay.b1, dff); put(a.g.W2, a.lay.W2, dff * D); put(a.g.b2, a.lay.b2, D);
+  put(a.g.Wo, a.lay.Wo, D * a.Fy); put(a.g.W_in, a.lay.W_in, a.win_elems); put(a.g.b_in, a.lay.b_in, D);
+  if (i0 == 0 && a.loss_sums) {
+    if (a.g.logvar_k) a.g.logvar_k[0] += (float)(-0.5 * a.loss_sums[0] * a.inv_n) + a.logdet_term;
+    if (a.g.logvar_q) a.g.logvar_q[0] += (float)(-0.5 * a.loss_sums[1] * a.inv_n) + a.logdet_term;
+    if (a.g.logvar_v) a.g.logvar_v[0] += (float)(-0.5 * a.loss_sums[2] * a.inv_n) + a.logdet_term;
+    if (a.g.logvar_z) a.g.logvar_z[0] += (float)(-0.5 * a.loss_sums[3] * a.inv_n) + a.logdet_term;
+  }
+}
+
+// Adam (tf.keras.optimizers.Adam: m, v moments, bias-corrected step size, epsilon outside the sqrt)
+__global__ void adam_kernel(long long n, float* p, const float* g, float* m, float* v, float lr_t, float b1, float b2, float eps) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float gi = g[i];
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi; v[i] = vi;
+    p[i] -= lr_t * mi / (sqrtf(vi) + eps);
+  }
+}
+
+}  // namespace smct

@@ -14,6 +14,7 @@
 #include "smct_fused.cuh"
 #include "smct_tc.cuh"
 #include "smct_fused_tc.cuh"
+#include "smct_backward.cuh"
 
 namespace {
 
@@ -360,6 +361,70 @@ int forward_fused(const smct_shape& s, const smct_params& pr, const smct_io& io,
   return SMCT_OK;
 }
 
+// ------------------------------------------------------------------------------------------
+// backward
+// ------------------------------------------------------------------------------------------
+smct::GradLayout make_layout(const smct_shape& s) {
+  smct::GradLayout l;
+  const int D = s.D, dff = s.dff;
+  int o = 0;
+  auto take = [&](int n) { int r = o; o += (n + 3) / 4 * 4; return r; };
+  l.Wq = take(D * D); l.bq = take(D); l.Wk = take(D * D); l.bk = take(D); l.Wv = take(D * D); l.bv = take(D);
+  l.Wz = take(D * D); l.bz = take(D); l.ln1_g = take(D); l.ln1_b = take(D); l.ln2_g = take(D); l.ln2_b = take(D);
+  l.W1 = take(D * dff); l.b1 = take(dff); l.W2 = take(dff * D); l.b2 = take(D); l.Wo = take(D * s.F_y);
+  l.W_in = take(s.input_mode == SMCT_INPUT_ENCODED ? 0 : s.F_x * D); l.b_in = take(D);
+  l.total = o;
+  return l;
+}
+
+constexpr int BWD_NREP = 296;
+
+int check_backward_shape(const smct_shape& s) {
+  if (s.H != 1 || !s.full_model || !s.noise_on || s.weights_mode != SMCT_WEIGHTS_GAUSSIAN || s.logvar_dim != 1 ||
+      s.noise_z_mode != SMCT_NOISE_Z_PYC)
+    return fail(SMCT_ERR_UNSUPPORTED, "backward supports: gaussian weights, 1 head, full model, scalar log-variances, noise_z_mode pyc");
+  if (s.D > 128) return fail(SMCT_ERR_UNSUPPORTED, "backward: d_model %d > 128", s.D);
+  if ((long long)s.S * s.D > 12800) return fail(SMCT_ERR_UNSUPPORTED, "backward: S*d_model %lld > 12800", (long long)s.S * s.D);
+  return SMCT_OK;
+}
+
+size_t backward_ws(const smct_shape& s) {
+  const size_t BSD = (size_t)s.B * s.S * s.D, BPS = (size_t)s.B * s.P * s.S;
+  const smct::GradLayout l = make_layout(s);
+  size_t n = 0;
+  n += 5 * align_up(BSD * 4);                                   // X, xln, q_, kx, vx
+  n += align_up((size_t)s.D * s.D * 4) + 2 * align_up((size_t)s.D * s.dff * 4);   // transposed weights
+  n += align_up(BPS * 2);                                       // anc
+  n += 2 * align_up(BPS * s.D * 4) + align_up(BPS * 2 * 4);     // Zm, dZm, stat
+  n += 6 * align_up(BSD * 4);                                   // per-row sums
+  n += align_up((size_t)BWD_NREP * l.total * 4) + align_up((size_t)l.total * 4);
+  return n + 1024;
+}
+
+template <int KD>
+int launch_backward_t(const smct::BwdArgs& a, cudaStream_t st) {
+  const int D = a.D, dff = a.dff;
+  const long long nrows = (long long)a.B * a.P * a.S;
+  smct::bwd_attn_fwd_kernel<KD><<<(int)std::min<long long>((nrows + 7) / 8, 148LL * 64), 256, 0, st>>>(a);
+  SMCT_LAUNCH_CHECK("bwd_attn_fwd_kernel");
+  const size_t smem_d = ((size_t)5 * smct::PT * (D + 1) + 2 * smct::PT * (dff + 1) + smct::PT + 7 * D + dff + D * a.Fy) * sizeof(float);
+  if (smem_d > 200 * 1024) return fail(SMCT_ERR_UNSUPPORTED, "backward dense tile needs %zu B shared memory", smem_d);
+  static bool attr_set = false;
+  if (!attr_set) {
+    SMCT_CUDA(cudaFuncSetAttribute(smct::bwd_dense_kernel<KD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    SMCT_CUDA(cudaFuncSetAttribute(smct::bwd_attn_bwd_kernel<KD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 205 * 1024));
+    attr_set = true;
+  }
+  const long long ntiles = (long long)a.B * a.S * ((a.P + smct::PT - 1) / smct::PT);
+  smct::bwd_dense_kernel<KD><<<(int)std::min<long long>(ntiles, a.nrep), smct::NT, smem_d, st>>>(a);
+  SMCT_LAUNCH_CHECK("bwd_dense_kernel");
+  const size_t smem_a = (size_t)4 * a.S * D * sizeof(float);
+  const int groups = (a.P + smct::BWD_PPC - 1) / smct::BWD_PPC;
+  smct::bwd_attn_bwd_kernel<KD><<<a.B * groups, 256, smem_a, st>>>(a);
+  SMCT_LAUNCH_CHECK("bwd_attn_bwd_kernel");
+  return SMCT_OK;
+}
+
 }  // namespace
 
 // ==========================================================================================
@@ -600,6 +665,101 @@ int smct_encode(const smct_shape* shape, const smct_params* params, const void* 
   ra.W_in = params->W_in; ra.b_in = params->b_in; ra.ln_g = params->ln1_g; ra.ln_b = params->ln1_b;
   ra.X = X; ra.xln = X_ln;
   return launch_rows(ra, (cudaStream_t)stream);
+}
+
+size_t smct_backward_workspace_bytes(const smct_shape* shape) {
+  if (check_shape(shape) != SMCT_OK) return 0;
+  if (check_backward_shape(*shape) != SMCT_OK) return 0;
+  return backward_ws(*shape);
+}
+
+int smct_backward(const smct_shape* shape, const smct_params* params, const smct_io* io, const smct_grads* grads,
+                  float inv_n, int32_t loss_variant, void* workspace, size_t workspace_bytes, void* stream) {
+  if (int rc = check_shape(shape)) return rc;
+  const smct_shape& s = *shape;
+  if (int rc = check_backward_shape(s)) return rc;
+  if (!params || !io || !grads) return fail(SMCT_ERR_INVALID, "params/io/grads is NULL");
+  if (!io->x_in || !io->y || !io->K || !io->V || !io->i_out)
+    return fail(SMCT_ERR_INVALID, "smct_backward needs io->x_in, y, K, V (final states) and i_out from the forward");
+  if (!(inv_n > 0.f)) return fail(SMCT_ERR_INVALID, "inv_n must be > 0");
+  if (!workspace || workspace_bytes < backward_ws(s)) return fail(SMCT_ERR_WORKSPACE, "workspace %zu < required %zu", workspace_bytes, backward_ws(s));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int B = s.B, P = s.P, S = s.S, D = s.D;
+  const size_t BSD = (size_t)B * S * D, BPS = (size_t)B * P * S;
+  const smct::GradLayout lay = make_layout(s);
+  Carver c{(char*)workspace, 0, workspace_bytes};
+  float* X = c.take<float>(BSD); float* xln = c.take<float>(BSD); float* q_ = c.take<float>(BSD);
+  float* kx = c.take<float>(BSD); float* vx = c.take<float>(BSD);
+  float* WzT = c.take<float>((size_t)D * D); float* W1T = c.take<float>((size_t)D * s.dff); float* W2T = c.take<float>((size_t)D * s.dff);
+  unsigned short* anc = c.take<unsigned short>(BPS);
+  float* Zm = c.take<float>(BPS * D); float* dZm = c.take<float>(BPS * D); float* stat = c.take<float>(BPS * 2);
+  float* sums = c.take<float>(6 * BSD);   // contiguous: one memset
+  float* rep = c.take<float>((size_t)BWD_NREP * lay.total);
+  float* flat = c.take<float>((size_t)lay.total);
+  // `sums` was carved as one block; re-derive the six (B,S,D) views without alignment gaps
+  float* dq_sum = sums; float* dk_sum = sums + BSD; float* dv_sum = sums + 2 * BSD; float* dxln_sum = sums + 3 * BSD;
+  float* dkx_sum = sums + 4 * BSD; float* dvx_sum = sums + 5 * BSD;
+  SMCT_CUDA(cudaMemsetAsync(sums, 0, 6 * BSD * sizeof(float), st));
+  SMCT_CUDA(cudaMemsetAsync(rep, 0, (size_t)BWD_NREP * lay.total * sizeof(float), st));
+  SMCT_CUDA(cudaMemsetAsync(flat, 0, (size_t)lay.total * sizeof(float), st));
+
+  smct::RowsArgs ra;
+  memset(&ra, 0, sizeof(ra));
+  ra.rows = (long long)B * S; ra.D = D; ra.Fx = s.F_x; ra.input_mode = s.input_mode; ra.do_ln = 1;
+  ra.sqrtD = sqrtf((float)D); ra.ln_eps = s.ln_eps; ra.x_in = io->x_in;
+  ra.W_in = params->W_in; ra.b_in = params->b_in; ra.ln_g = params->ln1_g; ra.ln_b = params->ln1_b;
+  ra.Wq = params->Wq; ra.bq = params->bq; ra.Wk = params->Wk; ra.bk = params->bk; ra.Wv = params->Wv; ra.bv = params->bv;
+  ra.X = X; ra.xln = xln; ra.q_ = q_; ra.kx = kx; ra.vx = vx;
+  if (int rc = launch_rows(ra, st)) return rc;
+  smct::transpose_kernel<<<64, 256, 0, st>>>(params->Wz, WzT, D, D);
+  SMCT_LAUNCH_CHECK("transpose_kernel");
+  smct::transpose_kernel<<<64, 256, 0, st>>>(params->W1, W1T, D, s.dff);
+  SMCT_LAUNCH_CHECK("transpose_kernel");
+  smct::transpose_kernel<<<64, 256, 0, st>>>(params->W2, W2T, s.dff, D);
+  SMCT_LAUNCH_CHECK("transpose_kernel");
+  smct::anc_trace_kernel<<<(int)std::min<long long>(((long long)B * P + 255) / 256, 148 * 8), 256, 0, st>>>(
+      B, P, S, s.len_resampling, io->i_out, anc);
+  SMCT_LAUNCH_CHECK("anc_trace_kernel");
+
+  smct::BwdArgs a;
+  memset(&a, 0, sizeof(a));
+  a.B = B; a.P = P; a.S = S; a.D = D; a.dff = s.dff; a.Fy = s.F_y; a.Fx = s.F_x; a.attn_window = s.attn_window;
+  a.len_resampling = s.len_resampling; a.input_mode = s.input_mode;
+  a.ln_eps = s.ln_eps; a.sigma_obs = s.sigma_obs; a.inv_n = inv_n; a.sqrtD = sqrtf((float)D);
+  a.b_global0 = s.b_global0; a.seed = io->seed;
+  a.x_in = io->x_in; a.X = X; a.xln = xln; a.q_ = q_; a.kx = kx; a.vx = vx;
+  a.y = (const float*)io->y; a.eps = io->eps; a.p = *params; a.WzT = WzT; a.W1T = W1T; a.W2T = W2T;
+  a.K = io->K; a.V = io->V; a.i_out = io->i_out; a.anc = anc; a.Zm = Zm; a.dZm = dZm; a.stat = stat;
+  a.dq_sum = dq_sum; a.dk_sum = dk_sum; a.dv_sum = dv_sum; a.dxln_sum = dxln_sum; a.dkx_sum = dkx_sum; a.dvx_sum = dvx_sum;
+  a.rep = rep; a.nrep = BWD_NREP; a.lay = lay;
+  int rc;
+  if (D <= 32) rc = launch_backward_t<1>(a, st);
+  else if (D <= 64) rc = launch_backward_t<2>(a, st);
+  else rc = launch_backward_t<4>(a, st);
+  if (rc) return rc;
+  const size_t smem_r = ((size_t)10 * D + 32) * sizeof(float);
+  smct::bwd_rows_kernel<<<(int)std::min<long long>((long long)B * S, BWD_NREP), 128, smem_r, st>>>(a);
+  SMCT_LAUNCH_CHECK("bwd_rows_kernel");
+  smct::reduce_replicas_kernel<<<(lay.total + 255) / 256, 256, 0, st>>>(rep, BWD_NREP, lay.total, flat);
+  SMCT_LAUNCH_CHECK("reduce_replicas_kernel");
+  smct::ScatterArgs sa;
+  memset(&sa, 0, sizeof(sa));
+  sa.lay = lay; sa.D = D; sa.dff = s.dff; sa.Fy = s.F_y; sa.win_elems = (s.input_mode == SMCT_INPUT_ENCODED) ? 0 : s.F_x * D;
+  sa.flat = flat; sa.loss_sums = io->loss_sums; sa.inv_n = inv_n;
+  sa.logdet_term = (loss_variant == SMCT_LOSS_CHECKOUT) ? 0.5f * D * (float)((double)B * P * S * inv_n) : 0.f;
+  sa.g = *grads;
+  smct::scatter_grads_kernel<<<64, 256, 0, st>>>(sa);
+  SMCT_LAUNCH_CHECK("scatter_grads_kernel");
+  return SMCT_OK;
+}
+
+int smct_adam_step(int64_t n, float* param, const float* grad, float* m, float* v, float lr_t, float beta1, float beta2,
+                   float epsilon, void* stream) {
+  if (n < 1 || !param || !grad || !m || !v) return fail(SMCT_ERR_INVALID, "smct_adam_step: bad arguments");
+  smct::adam_kernel<<<(int)std::min<long long>((n + 255) / 256, 148 * 8), 256, 0, (cudaStream_t)stream>>>(
+      n, param, grad, m, v, lr_t, beta1, beta2, epsilon);
+  SMCT_LAUNCH_CHECK("adam_kernel");
+  return SMCT_OK;
 }
 
 int smct_tc_selftest(const float* A, const float* W, float* D, void* scratch, void* stream) {

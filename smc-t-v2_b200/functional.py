@@ -7,7 +7,7 @@ from typing import Dict, Optional
 import torch
 
 from . import _lib
-from ._lib import ALGO, INPUT, NOISE_Z, WEIGHTS, SmctIO, SmctParams, SmctShape, check
+from ._lib import ALGO, INPUT, LOSS, NOISE_Z, WEIGHTS, SmctGrads, SmctIO, SmctParams, SmctShape, check
 
 _ws_cache: Dict[int, torch.Tensor] = {}
 
@@ -315,3 +315,57 @@ def tc_selftest(A: torch.Tensor, W: torch.Tensor) -> torch.Tensor:
     scratch = torch.empty(16384 + 256, dtype=torch.uint8, device=A.device)
     check(lib.smct_tc_selftest(_ptr(A, torch.float32, "A"), _ptr(W, torch.float32, "W"), _ptr(D), _ptr(scratch), _stream()))
     return D
+
+
+_bws_cache: Dict[int, torch.Tensor] = {}
+
+
+def backward(shape: SmctShape, params: Dict[str, torch.Tensor], x_in: torch.Tensor, y: torch.Tensor, fwd: dict,
+             eps: Optional[torch.Tensor] = None, seed: int = 0, inv_n: Optional[float] = None, loss_variant="pyc",
+             grads: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
+    """tape.gradient(loss, trainable_variables) through smct_backward.  `fwd` is the dict returned by forward()
+    on the same shape/params/inputs/randomness with want=("i_out","loss_sums").  Gradients are accumulated into
+    `grads` (created zero-filled when None).  inv_n defaults to 1/(B*P*S) of this call."""
+    require_cuda()
+    lib = _lib.load()
+    dev = x_in.device
+    if grads is None:
+        grads = {n: torch.zeros_like(t) for n, t in params.items() if n in _lib.PARAM_FIELDS}
+    g = SmctGrads()
+    for n in _lib.GRAD_FIELDS:
+        setattr(g, n, _ptr(grads.get(n), torch.float32, "grad " + n))
+    io = SmctIO()
+    x_dtype = torch.int32 if shape.input_mode == INPUT["embedding"] else torch.float32
+    io.x_in = _ptr(x_in, x_dtype, "x_in")
+    io.y = _ptr(y, torch.float32, "y")
+    io.eps = _ptr(eps, torch.float32, "eps")
+    io.seed = int(seed)
+    io.K = _ptr(fwd["K"], torch.float32, "K")
+    io.V = _ptr(fwd["V"], torch.float32, "V")
+    io.i_out = _ptr(fwd["i_out"], torch.int32, "i_out")
+    io.loss_sums = _ptr(fwd.get("loss_sums"), torch.float64, "loss_sums")
+    need = lib.smct_backward_workspace_bytes(ctypes.byref(shape))
+    if need == 0:
+        raise _lib.SmctError(-4, lib.smct_last_error().decode())
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    ws = _bws_cache.get(key)
+    if ws is None or ws.numel() < need:
+        _bws_cache.pop(key, None)
+        ws = torch.empty(need, dtype=torch.uint8, device=dev)
+        _bws_cache[key] = ws
+    if inv_n is None:
+        inv_n = 1.0 / (float(shape.B) * shape.P * shape.S)
+    ps = params_struct(params, shape)
+    check(lib.smct_backward(ctypes.byref(shape), ctypes.byref(ps), ctypes.byref(io), ctypes.byref(g), float(inv_n),
+                            LOSS[loss_variant], ctypes.c_void_p(ws.data_ptr()), ws.numel(), _stream()))
+    return grads
+
+
+def adam_step(param: torch.Tensor, grad: torch.Tensor, m: torch.Tensor, v: torch.Tensor, lr_t: float, beta1=0.9,
+              beta2=0.98, epsilon=1e-9):
+    """One tf.keras Adam update of a parameter tensor, in place (lr_t already bias-corrected)."""
+    require_cuda()
+    lib = _lib.load()
+    check(lib.smct_adam_step(param.numel(), _ptr(param, torch.float32, "param"), _ptr(grad, torch.float32, "grad"),
+                             _ptr(m, torch.float32, "m"), _ptr(v, torch.float32, "v"), float(lr_t), float(beta1),
+                             float(beta2), float(epsilon), _stream()))
