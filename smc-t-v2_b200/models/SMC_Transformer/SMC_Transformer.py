@@ -53,7 +53,10 @@ class SMC_Transformer:
         self.dff = dff
         self.task = task
         self.training = False
-        self.noise_z_mode = "checkout"   # "pyc" reproduces the regression-era noise_z = z - dense(z_)
+        # noise_z recorded for the loss: None -> "pyc" (regression era, z - dense(z_)) for float inputs,
+        # "checkout" (z - z_, self_attention_SMC.py:190) for integer tokens.  Gradients need "pyc".
+        self.noise_z_mode = None
+        self._last_forward = None
         self.algo = "auto"
         self.seed = None                 # int -> reproducible draws; None -> fresh Philox seed per call
         self._rng = np.random.default_rng(seed)
@@ -113,7 +116,8 @@ class SMC_Transformer:
                             dff=self.dff, F_x=F_x, F_y=F_y, full_model=self.full_model,
                             attn_window=c.attention_smc.attn_window, len_resampling=c.len_resampling,
                             weights="classification" if task == "classification" else "gaussian",
-                            noise_z_mode=self.noise_z_mode, input_mode="embedding" if task == "classification" else "linear",
+                            noise_z_mode=self.noise_z_mode or ("checkout" if task == "classification" else "pyc"),
+                            input_mode="embedding" if task == "classification" else "linear",
                             noise=c.noise, logvar_dim=c.attention_smc.logvar_dim(), algo=self.algo,
                             sigma_obs=c.Sigma_obs, b_global0=b_global0)
 
@@ -174,9 +178,12 @@ class SMC_Transformer:
         dev = _device()
         cvt = lambda a, dt: None if a is None else _as_tensor(a).to(dev, dt).contiguous()
         want = ("i_out", "noise_q", "noise_z", "noise_K", "noise_V", "loss_sums") if self.cell.noise else ("noise_K", "noise_V")
-        out = F.forward(shape, self._params(task, F_x), x, y, eps=cvt(eps, torch.float32), u=cvt(u, torch.float64),
-                        i_forced=cvt(i_forced, torch.int32), seed=self.seed if self.seed is not None else next_seed(),
-                        want=want)
+        params = self._params(task, F_x)
+        seed = self.seed if self.seed is not None else next_seed()
+        eps_t = cvt(eps, torch.float32)
+        out = F.forward(shape, params, x, y, eps=eps_t, u=cvt(u, torch.float64), i_forced=cvt(i_forced, torch.int32),
+                        seed=seed, want=want)
+        self._last_forward = dict(shape=shape, params=params, x=x, y=y, out=out, eps=eps_t, seed=seed)
         self.cell.dec_timestep = 0   # SMC_Transformer.py:214-215
         self.cell.cell_count = 0
         self.noise_K_resampled = out["noise_K"]

@@ -1,31 +1,59 @@
 """Mirror of src/train/train_step_functions.py:31-68 (train_step_SMC_T).
 
-The forward pass, the SMC loss, the EM variance update and the metric run on the CUDA path.  The
-gradient step needs the backward pass of the particle filter (reverse-time sweep with scatter-add over
-ancestors), which is SURVEY.md §8(f) rank 1 and not built yet: passing an optimizer raises."""
+Forward, SMC loss, EM variance update, metric, gradients (smct_backward) and the Adam step all run on the CUDA
+path.  With several ranks (torch.distributed initialised) the gradients of the batch shards are all-reduced over
+NCCL before the update (one flat buffer), so every rank applies the same step."""
 import torch
 
+from .. import distributed as D
+from .. import functional as F
 from .utils import EM, compute_categorical_cross_entropy, compute_mse_metric
 
 
+def compute_gradients(smc_transformer, inputs, targets, inv_n=None, loss_variant="pyc"):
+    """tape.gradient(loss, trainable_variables) for the forward pass that was just run on (inputs, targets).
+    Returns {parameter name: gradient tensor} keyed like smct_params."""
+    m = smc_transformer
+    fwd = m._last_forward
+    if fwd is None:
+        raise RuntimeError("call the model on (inputs, targets) before compute_gradients")
+    return F.backward(fwd["shape"], fwd["params"], fwd["x"], fwd["y"], fwd["out"], eps=fwd["eps"], seed=fwd["seed"],
+                      inv_n=inv_n, loss_variant=loss_variant)
+
+
 def train_step_SMC_T(inputs, targets, smc_transformer, optimizer, it, attention_mask=None, EM_param=None):
-    """Same signature/return as the reference: (loss, metric-or-None)."""
+    """Same signature/return as the reference: (loss, metric-or-None).  optimizer=None: forward + loss only."""
     (preds, preds_resampl), _, _ = smc_transformer(inputs=inputs, targets=targets, attention_mask=attention_mask)
     if EM_param is not None:
         smc_transformer = EM(smc_transformer, it=it, EM_param=EM_param)
     smc_loss, classic_loss = smc_transformer.compute_SMC_loss(predictions=preds_resampl, inputs=inputs, targets=targets,
                                                               attention_mask=attention_mask)
     loss = smc_loss
-    if torch.is_floating_point(torch.as_tensor(targets)):
+    regression = torch.is_floating_point(torch.as_tensor(targets))
+    if regression:
         metric = compute_mse_metric(targets, preds)
     else:
         metric = compute_categorical_cross_entropy(targets=targets, preds=preds,
                                                    num_particles=smc_transformer.cell.num_particles,
                                                    attention_mask=attention_mask)
     if optimizer is not None:
-        raise NotImplementedError(
-            "gradient step: the backward pass of the SMC forward is not built yet (SURVEY.md §8(f) rank 1); "
-            "call with optimizer=None for forward + loss (+ EM variance update)")
+        if not regression:
+            raise NotImplementedError("gradients are built for the regression (gaussian-weight) SMC-T; the classification "
+                                      "checkout variant is forward-only")
+        rank, world = D.world()
+        B, P, S = preds.shape[0], preds.shape[1], preds.shape[2]
+        grads = compute_gradients(smc_transformer, inputs, targets, inv_n=1.0 / (float(B) * world * P * S))
+        names = sorted(grads)
+        if world > 1:
+            flat = torch.cat([grads[n].reshape(-1) for n in names])
+            D.allreduce_sums(flat)
+            o = 0
+            for n in names:
+                k = grads[n].numel()
+                grads[n].copy_(flat[o:o + k].reshape(grads[n].shape))
+                o += k
+        params = smc_transformer._last_forward["params"]
+        optimizer.apply_gradients((grads[n], params[n]) for n in names)
     if smc_transformer.cell.noise:
         return loss, metric
     return loss, None

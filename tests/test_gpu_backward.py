@@ -96,3 +96,22 @@ def test_adam_step_matches_keras_formula():
         pm = b1 * pm + (1 - b1) * g; pv = b2 * pv + (1 - b2) * g.astype(np.float64) ** 2
         pp = pp - lr_t * pm / (np.sqrt(pv) + eps)
     assert np.allclose(p.cpu().numpy(), pp, rtol=1e-5, atol=1e-6)
+
+
+def test_training_reduces_the_loss():
+    """train_step_SMC_T with the mirrored Adam: a few hundred steps on a small AR(1) batch with FIXED draws
+    (model.seed) must lower the SMC loss — gradients, optimizer and parameter plumbing end to end."""
+    from smct_b200.models.SMC_Transformer.SMC_Transformer import SMC_Transformer
+    from smct_b200.train.optimizers import Adam
+    from smct_b200.train.train_step_functions import train_step_SMC_T
+    from smct_b200 import utils
+    x, y = utils.synthetic_ar1(16, 24, 1, alpha=0.8, var=0.5)
+    inputs, targets = torch.from_numpy(x).unsqueeze(1), torch.from_numpy(y).unsqueeze(1)
+    model = SMC_Transformer(d_model=8, output_size=1, seq_len=24, full_model=True, dff=8)
+    model.cell.add_SMC_parameters(dict_sigmas=dict(k=0.5, q=0.5, v=0.5, z=0.5), num_particles=10, sigma_obs=0.5)
+    model.seed = 1234
+    opt = Adam(learning_rate=5e-3, beta_1=0.9, beta_2=0.98, epsilon=1e-9)
+    first = float(train_step_SMC_T(inputs, targets, model, opt, it=1)[0])
+    for it in range(2, 150):
+        loss, metric = train_step_SMC_T(inputs, targets, model, opt, it=it)
+    assert float(loss) < 0.9 * first, (first, float(loss))

@@ -42,6 +42,7 @@ def _build_mirror(g, cfg, p):
                                   sigma_obs=cfg.sigma_obs)
     if cfg.len_resampling is not None:
         model.cell.add_stop_resampling(cfg.len_resampling)
+    model.noise_z_mode = "checkout"   # the fixtures were written by the checkout's cell code (noise_z = z - z_)
     att, c = model.cell.attention_smc, model.cell
     for layer, (W, b) in ((att.wq, ("Wq", "bq")), (att.wk, ("Wk", "bk")), (att.wv, ("Wv", "bv")), (att.dense, ("Wz", "bz")),
                           (c.ffn.dense1, ("W1", "b1")), (c.ffn.dense2, ("W2", "b2"))):
@@ -142,8 +143,14 @@ def test_train_step_mirror_forward_loss_and_em():
     lv0 = float(model.cell.attention_smc.logvar_k.numpy())
     loss2, _ = train_step_SMC_T(inputs, targets, model, None, it=2, EM_param=0.6)
     assert float(model.cell.attention_smc.logvar_k.numpy()) != lv0          # EM moved the variance
-    with pytest.raises(NotImplementedError):
-        train_step_SMC_T(inputs, targets, model, object(), it=3)             # backward not built yet
+    # a real optimisation step: gradients through smct_backward, Adam through smct_adam_step
+    from smct_b200.train.optimizers import Adam, CustomSchedule
+    model.noise_z_mode = None                                                # regression-era noise_z (needed by the backward)
+    opt = Adam(CustomSchedule(cfg.D), beta_1=0.9, beta_2=0.98, epsilon=1e-9)
+    w_before = model.cell.ffn.dense1.kernel.numpy().copy()
+    model.seed = 9
+    losses = [float(train_step_SMC_T(inputs, targets, model, opt, it=i + 3)[0]) for i in range(3)]
+    assert np.all(np.isfinite(losses)) and not np.array_equal(model.cell.ffn.dense1.kernel.numpy(), w_before)
 
 
 def test_smct_algo_wiring():
