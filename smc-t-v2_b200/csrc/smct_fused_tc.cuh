@@ -40,6 +40,16 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 __device__ __forceinline__ void copy_block_async(unsigned char* dst, const unsigned char* src, int bytes) {
   for (int i = threadIdx.x; i < bytes / 16; i += FNT) cp_async16(dst + 16 * i, src + 16 * i);
 }
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+// lane l4 of a particle prefetches one 256-byte row (two lines) of the slot pair starting at s: lanes 0,1 -> K,V of
+// slot s, lanes 2,3 -> K,V of slot s+1
+__device__ __forceinline__ void prefetch_rows(const float* Kb, const float* Vb, int slot, int row, int P, int l4) {
+  const float* base = ((l4 & 1) ? Vb : Kb) + (size_t)((uint32_t)(slot * P + row) * FD);
+  prefetch_l2(base);
+  prefetch_l2(base + 32);
+}
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -157,6 +167,15 @@ __global__ void __launch_bounds__(FNT, 1) fused_tc_forward_kernel(const FusedArg
         const unsigned long long gbp = (unsigned long long)(a.b_global0 + b) * (unsigned long long)P + L;
         const long long lrow = ((bP + L) * S + t) * FD;
         const uint32_t prow = (uint32_t)(t * P + qc) * FD;
+        const unsigned short* Arow = Acur + (long long)qc * Sa;
+        const int nfull = (t - s_lo) / FSB;   // blocks made only of slots < t
+        {  // L2 prefetch of the first history blocks: they travel while the noise is generated
+          const int npro = min(a.pf_pro, nfull);
+          for (int pb = 0; pb < npro; ++pb) {
+            const int sp = s_lo + pb * FSB + (l4 >> 1);
+            prefetch_rows(Kb, Vb, sp, (int)Arow[sp], P, l4);
+          }
+        }
         float4 qv[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -197,17 +216,17 @@ __global__ void __launch_bounds__(FNT, 1) fused_tc_forward_kernel(const FusedArg
           if (act) {
             *reinterpret_cast<float4*>(Kb + prow + d0) = make_float4(ko[0], ko[1], ko[2], ko[3]);
             *reinterpret_cast<float4*>(Vb + prow + d0) = make_float4(vo[0], vo[1], vo[2], vo[3]);
-            if (a.noise_q) *reinterpret_cast<float4*>(a.noise_q + lrow + d0) = make_float4(nq[0], nq[1], nq[2], nq[3]);
+            if (a.noise_q) __stcs(reinterpret_cast<float4*>(a.noise_q + lrow + d0), make_float4(nq[0], nq[1], nq[2], nq[3]));
           }
         }
         // causal attention over the genealogy: slot s lives in physical row A[q][s] (s < t) or q (s == t)
-        const unsigned short* Arow = Acur + (long long)qc * Sa;
         float m = -INFINITY, l = 0.f;
         float4 zacc[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) zacc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        const int nfull = (t - s_lo) / FSB;   // blocks made only of slots < t
         int s = s_lo;
+        const int pfd = a.pf_dist;
+        int rpf = (pfd > 0 && pfd < nfull) ? (int)Arow[s_lo + pfd * FSB + (l4 >> 1)] : 0;
         int rn[FSB];
 #pragma unroll
         for (int j = 0; j < FSB; ++j) rn[j] = (nfull > 0) ? (int)Arow[s_lo + j] : 0;
@@ -219,17 +238,21 @@ __global__ void __launch_bounds__(FNT, 1) fused_tc_forward_kernel(const FusedArg
 #pragma unroll
             for (int j = 0; j < FSB; ++j) rn[j] = (int)Arow[s + FSB + j];
           }
+          if (pfd > 0 && blk + pfd < nfull) {
+            prefetch_rows(Kb, Vb, s + pfd * FSB + (l4 >> 1), rpf, P, l4);
+            if (blk + pfd + 1 < nfull) rpf = (int)Arow[s + (pfd + 1) * FSB + (l4 >> 1)];
+          }
           float sc[FSB];
           float4 vr[FSB][4];
 #pragma unroll
           for (int j = 0; j < FSB; ++j) {
-            float part = 0.f;
+            float4 kr[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              const float4 kr = *reinterpret_cast<const float4*>(Kb + off[j] + 16 * i);
+              kr[i] = *reinterpret_cast<const float4*>(Kb + off[j] + 16 * i);
               vr[j][i] = *reinterpret_cast<const float4*>(Vb + off[j] + 16 * i);
-              part = dot4(qv[i], kr, part);
             }
+            float part = dot4(qv[1], kr[1], dot4(qv[0], kr[0], 0.f)) + dot4(qv[3], kr[3], dot4(qv[2], kr[2], 0.f));
             part += __shfl_xor_sync(SMCT_FULL_MASK, part, 1);
             part += __shfl_xor_sync(SMCT_FULL_MASK, part, 2);
             sc[j] = part;
@@ -326,7 +349,7 @@ __global__ void __launch_bounds__(FNT, 1) fused_tc_forward_kernel(const FusedArg
             s1 += val[4 * gq + e];
           }
           if (eact && a.noise_z)
-            *reinterpret_cast<float4*>(a.noise_z + ((bP + eL) * S + t) * FD + n) = make_float4(nzv[0], nzv[1], nzv[2], nzv[3]);
+            __stcs(reinterpret_cast<float4*>(a.noise_z + ((bP + eL) * S + t) * FD + n), make_float4(nzv[0], nzv[1], nzv[2], nzv[3]));
         }
         sm.psum[0][ecq][er] = s1;
         __syncthreads();
@@ -430,7 +453,7 @@ __global__ void __launch_bounds__(FNT, 1) fused_tc_forward_kernel(const FusedArg
             r4[e] = val[4 * gq + e] * inv + (sm.ln2b[n + e] - mean * inv);
           }
           *reinterpret_cast<float4*>(&sm.Os[er * FLD + n]) = make_float4(r4[0], r4[1], r4[2], r4[3]);
-          if (eact) *reinterpret_cast<float4*>(rrow + n) = make_float4(r4[0], r4[1], r4[2], r4[3]);
+          if (eact) __stcs(reinterpret_cast<float4*>(rrow + n), make_float4(r4[0], r4[1], r4[2], r4[3]));   // read again only by the final pass
         }
       }
       tc::fence_before_sync();

@@ -164,3 +164,28 @@ def test_smct_algo_wiring():
     (pred, pred_r), (K, V, R), w = m(x, x)
     assert tuple(pred.shape) == (32, 10, 24, 1) and tuple(K.shape) == (32, 10, 24, 8)
     assert np.allclose(w.sum(1).cpu().numpy(), 1.0, atol=1e-4)
+
+
+def test_forecasting_helpers():
+    """Regression-era inference helpers (src/eval/inference_functions.py): one-step with resampling stopped,
+    incremental multi-step roll-out on the particles' K/V cache."""
+    from smct_b200.eval.inference_functions import (get_distrib_all_timesteps, inference_multistep, inference_onestep,
+                                                     split_input_target)
+    from smct_b200.models.SMC_Transformer.SMC_Transformer import SMC_Transformer
+    from smct_b200 import utils
+    x, _ = utils.synthetic_ar1(6, 31, 1, alpha=0.8, var=0.5)
+    data = torch.from_numpy(x).unsqueeze(1)                       # (B,1,31,1)
+    inputs, targets = split_input_target(data)                    # (B,1,30,1)
+    model = SMC_Transformer(d_model=8, output_size=1, seq_len=30, full_model=True, dff=8)
+    model.cell.add_SMC_parameters(dict_sigmas=dict(k=0.1, q=0.1, v=0.1, z=0.1), num_particles=20, sigma_obs=0.5)
+    preds_future, mean_preds = inference_onestep(model, inputs, targets, None, past_len=20)
+    assert tuple(preds_future.shape) == (6, 20, 10, 1) and tuple(mean_preds.shape) == (6, 30, 1)
+    assert model.cell.len_resampling == 20
+    # after past_len the genealogy is frozen: K rows of slots >= past_len are the particles' own rows
+    pf, mean = inference_multistep(model, inputs[:, :, :20], targets[:, :, :20], past_len=20, future_len=10, seed=3)
+    assert tuple(pf.shape) == (6, 20, 10, 1) and tuple(mean.shape) == (6, 10, 1) and torch.isfinite(pf).all()
+    pf2, _ = inference_multistep(model, inputs[:, :, :20], targets[:, :, :20], past_len=20, future_len=10, seed=3)
+    assert torch.equal(pf, pf2)                                   # seeded roll-out is reproducible
+    d = get_distrib_all_timesteps(pf, sigma_obs=0.5, P=20, save_path_distrib=None, N_est=7, len_future=10,
+                                  rng=np.random.default_rng(0))
+    assert d.shape == (6, 7, 10, 1)
