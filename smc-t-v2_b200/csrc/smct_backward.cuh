@@ -9,12 +9,19 @@
 // loss is a sum over B*P independent "paths": each path is one causal-attention + LN/FFN/LN + linear-head
 // sequence of length S whose inputs (x rows, noise constants) are known.  The backward is therefore driven
 // entirely by the forward's OUTPUTS (K, V final; ancestor indices; the RNG seed or injected eps) and needs no
-// genealogy bookkeeping: rows shared by several final particles are simply processed once per path.
+// genealogy bookkeeping.
+// Node de-duplication.  Paths that share the ancestor at slot s share the whole prefix 0..s, hence the row
+// (q_s, z_s, r_s, pred_s) and every derivative of it: the loss is a sum over the NODES (s, ancestor) of the final
+// genealogy tree, each weighted by the number m of final particles that descend from it.  node_*_kernel build
+// the compact node list (representative final particle, logical ancestor id, multiplicity); all row-wise
+// kernels below run once per node with the loss gradient scaled by m.  With resampling at every step the tree
+// has a few thousand nodes per sequence instead of P*S rows; without resampling every row is its own node.
 //   noise constants:  k_s - k_(x_s) and v_s - v_(x_s) are recovered from the stored rows;
 //                     eps_q / eps_z of row (path p, slot s) belong to the logical particle anc[b,p,s] that p
 //                     descends from at time s (traced from i_out) and are regenerated (Philox) or read (eps).
 // Kernels (correctness-first, generic d_model <= 128, 1 head, full model):
-//   anc_trace_kernel        lineage of every final particle in logical ids
+//   anc_trace_kernel        lineage of every final particle in logical ids, (B,S,P)
+//   node_count/scan/fill    unique (slot, ancestor) nodes per (b,s): representative particle, multiplicity
 //   bwd_attn_fwd_kernel     recompute q, attention output z_ and the softmax statistics per row
 //   bwd_dense_kernel        per 32-particle tile at one (b,s): recompute dense forward, back-propagate to dz_,
 //                           weight gradients into CTA-private replicas (no float atomics on weights)
@@ -46,8 +53,13 @@ struct BwdArgs {
   const float *WzT, *W1T, *W2T;           // transposed weights
   const float *K, *V;                     // (B,P,S,D) final states
   const int* i_out;                       // (S,B,P)
-  unsigned short* anc;                    // (B,P,S)
-  float *Zm, *dZm, *stat;                 // (B,P,S,D), (B,P,S,D), (B,P,S,2)
+  unsigned short* anc;                    // (B,S,P) logical ancestor of final particle p at slot s
+  // compact node list (nodes of (b,s) occupy [node_off[b*S+s], node_off[b*S+s+1]), ordered by ancestor id)
+  const int* node_off;                    // (B*S+1)
+  const int* node_bs;                     // (N) b*S+s
+  const unsigned short *node_p, *node_L;  // (N) representative final particle, logical ancestor id
+  const float* node_m;                    // (N) multiplicity
+  float *Zm, *dZm, *stat;                 // (N,D), (N,D), (N,2) per node
   float *dq_sum, *dk_sum, *dv_sum, *dxln_sum, *dkx_sum, *dvx_sum;   // (B,S,D)
   float* rep;                             // nrep x layout.total gradient replicas
   int nrep;
@@ -61,8 +73,90 @@ __global__ void anc_trace_kernel(int B, int P, int S, int len_resampling, const 
     int l = (int)(bp % P);
     for (int t = S - 1; t >= 0; --t) {
       if (len_resampling < 0 || t < len_resampling) l = i_out[((long long)t * B + b) * P + l];
-      anc[bp * S + t] = (unsigned short)l;
+      anc[((long long)b * S + t) * P + (bp % P)] = (unsigned short)l;
     }
+  }
+}
+
+
+// Histogram of the ancestors at slot s over the final particles of sequence b (one CTA per (b,s)).
+// cnt[L] = multiplicity, rep[L] = smallest final particle descending from L.  Returns the number of nodes.
+__device__ __forceinline__ int node_histogram(int P, const unsigned short* anc_bs, int* cnt, int* rep, int* scratch) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int i = tid; i < P; i += nt) { cnt[i] = 0; rep[i] = 0x7fffffff; }
+  __syncthreads();
+  for (int p = tid; p < P; p += nt) {
+    const int L = anc_bs[p];
+    atomicAdd(&cnt[L], 1);
+    atomicMin(&rep[L], p);
+  }
+  __syncthreads();
+  int local = 0;
+  for (int i = tid; i < P; i += nt) local += (cnt[i] > 0);
+  local = __reduce_add_sync(SMCT_FULL_MASK, local);
+  if ((tid & 31) == 0) scratch[tid >> 5] = local;
+  __syncthreads();
+  int total = 0;
+  for (int w = 0; w < (nt >> 5); ++w) total += scratch[w];
+  return total;
+}
+
+__global__ void __launch_bounds__(256) node_count_kernel(int P, const unsigned short* anc, int* node_cnt) {
+  extern __shared__ int nsm[];
+  __shared__ int scratch[8];
+  const int total = node_histogram(P, anc + (long long)blockIdx.x * P, nsm, nsm + P, scratch);
+  if (threadIdx.x == 0) node_cnt[blockIdx.x] = total;
+}
+
+// exclusive scan of n counts (one CTA of 1024 threads); off[n] = total
+__global__ void __launch_bounds__(1024) node_scan_kernel(int n, const int* cnt, int* off) {
+  __shared__ int part[1024];
+  const int tid = threadIdx.x;
+  const int per = (n + 1023) / 1024;
+  const int i0 = min(n, tid * per), i1 = min(n, i0 + per);
+  int sum = 0;
+  for (int i = i0; i < i1; ++i) sum += cnt[i];
+  part[tid] = sum;
+  __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) {
+    const int v = (tid >= o) ? part[tid - o] : 0;
+    __syncthreads();
+    part[tid] += v;
+    __syncthreads();
+  }
+  int run = part[tid] - sum;
+  for (int i = i0; i < i1; ++i) { off[i] = run; run += cnt[i]; }
+  if (tid == 1023) off[n] = part[1023];
+}
+
+__global__ void __launch_bounds__(256) node_fill_kernel(int P, const unsigned short* anc, const int* node_off,
+                                                        int* node_bs, unsigned short* node_p, unsigned short* node_L,
+                                                        float* node_m) {
+  extern __shared__ int nsm[];
+  __shared__ int scratch[8];
+  __shared__ int wbase[9];
+  int* cnt = nsm;
+  int* rep = nsm + P;
+  node_histogram(P, anc + (long long)blockIdx.x * P, cnt, rep, scratch);
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  int base = node_off[blockIdx.x];
+  for (int i0 = 0; i0 < P; i0 += 256) {      // ordered compaction, 256 ancestors per pass
+    const int i = i0 + tid;
+    const bool live = (i < P) && (cnt[i] > 0);
+    const unsigned bal = __ballot_sync(SMCT_FULL_MASK, live);
+    __syncthreads();
+    if (lane == 0) wbase[wid + 1] = __popc(bal);
+    __syncthreads();
+    if (tid == 0) { wbase[0] = 0; for (int w = 0; w < 8; ++w) wbase[w + 1] += wbase[w]; }
+    __syncthreads();
+    if (live) {
+      const int u = base + wbase[wid] + __popc(bal & ((1u << lane) - 1u));
+      node_bs[u] = blockIdx.x;
+      node_p[u] = (unsigned short)rep[i];
+      node_L[u] = (unsigned short)i;
+      node_m[u] = (float)cnt[i];
+    }
+    base += wbase[8];
   }
 }
 
@@ -81,26 +175,26 @@ __device__ __forceinline__ float bwd_eps(const BwdArgs& a, int which, int b, int
 }
 
 // ------------------------------------------------------------------------------------------
-// attention forward recompute: one warp per row (b,p,s)
+// attention forward recompute: one warp per node (b, s, ancestor)
 // ------------------------------------------------------------------------------------------
 template <int KD>
 __global__ void __launch_bounds__(256) bwd_attn_fwd_kernel(const BwdArgs a) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int D = a.D, S = a.S;
-  const long long nrows = (long long)a.B * a.P * S;
+  const long long nnodes = a.node_off[a.B * S];
   const float std_q = expf(0.5f * a.p.logvar_q[0]);
   const float sqrt_d = sqrtf((float)D);
-  for (long long row = (long long)blockIdx.x * 8 + wid; row < nrows; row += (long long)gridDim.x * 8) {
-    const int s = (int)(row % S);
-    const long long bp = row / S;
-    const int b = (int)(bp / a.P);
-    const int L = a.anc[row];
+  for (long long u = (long long)blockIdx.x * 8 + wid; u < nnodes; u += (long long)gridDim.x * 8) {
+    const int bs = a.node_bs[u];
+    const int s = bs % S, b = bs / S;
+    const long long bp = (long long)b * a.P + a.node_p[u];
+    const int L = a.node_L[u];
     const int s_lo = (a.attn_window >= 0 && s > a.attn_window) ? s - a.attn_window : 0;
     float q[KD], acc[KD];
 #pragma unroll
     for (int k = 0; k < KD; ++k) {
       const int d = lane + 32 * k;
-      q[k] = (d < D) ? __fadd_rn(a.q_[((long long)b * S + s) * D + d], __fmul_rn(std_q, bwd_eps(a, 1, b, s, L, d))) : 0.f;
+      q[k] = (d < D) ? __fadd_rn(a.q_[(long long)bs * D + d], __fmul_rn(std_q, bwd_eps(a, 1, b, s, L, d))) : 0.f;
       acc[k] = 0.f;
     }
     const float* Kp = a.K + bp * S * D;
@@ -126,14 +220,15 @@ __global__ void __launch_bounds__(256) bwd_attn_fwd_kernel(const BwdArgs a) {
 #pragma unroll
     for (int k = 0; k < KD; ++k) {
       const int d = lane + 32 * k;
-      if (d < D) a.Zm[row * D + d] = acc[k] / l;
+      if (d < D) a.Zm[u * D + d] = acc[k] / l;
     }
-    if (lane == 0) { a.stat[row * 2] = m; a.stat[row * 2 + 1] = l; }
+    if (lane == 0) { a.stat[u * 2] = m; a.stat[u * 2 + 1] = l; }
   }
 }
 
 // ------------------------------------------------------------------------------------------
-// dense forward recompute + backward: persistent CTAs, one tile = 32 particles at one (b,s)
+// dense forward recompute + backward: persistent CTAs, one tile = 32 consecutive nodes of the flat node list
+// (a tile may span several (b,s); every row carries its own b*S+s, ancestor id and multiplicity)
 // ------------------------------------------------------------------------------------------
 // rep[(k,n)] += sum_rows A[row][k] * Bm[row][n]   (CTA-private replica: plain read-modify-write)
 __device__ __forceinline__ void tile_outer_accum(const float* A, int lda, const float* Bm, int ldb, int Kdim, int N, float* rep) {
@@ -149,7 +244,7 @@ __device__ __forceinline__ void tile_outer_accum(const float* A, int lda, const 
 template <int KD>
 __global__ void __launch_bounds__(NT) bwd_dense_kernel(const BwdArgs a) {
   extern __shared__ float sm[];
-  const int D = a.D, Dp = D + 1, dff = a.dff, Fp = dff + 1, S = a.S, P = a.P, Fy = a.Fy;
+  const int D = a.D, Dp = D + 1, dff = a.dff, Fp = dff + 1, S = a.S, Fy = a.Fy;
   float* Zt = sm;                 // z_ tile
   float* Ut = Zt + PT * Dp;       // normalised LN1 input (u hat)
   float* Ot = Ut + PT * Dp;       // o = LN1(z + x)
@@ -167,20 +262,25 @@ __global__ void __launch_bounds__(NT) bwd_dense_kernel(const BwdArgs a) {
   float* rep = a.rep + (long long)blockIdx.x * a.lay.total;
   const float std_z = expf(0.5f * a.p.logvar_z[0]);
   const float c_obs = a.inv_n / a.sigma_obs;
+  __shared__ int rbs[PT], rL[PT];
+  __shared__ float rm[PT];
   for (int i = tid; i < n_small; i += NT) g_small[i] = 0.f;
-  const int ptiles = (P + PT - 1) / PT;
-  const long long ntiles = (long long)a.B * S * ptiles;
+  const long long nnodes = a.node_off[a.B * S];
+  const long long ntiles = (nnodes + PT - 1) / PT;
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int pt = (int)(tile % ptiles);
-    const long long bs = tile / ptiles;
-    const int s = (int)(bs % S), b = (int)(bs / S);
-    const int p0 = pt * PT, np = min(PT, P - p0);
-    const float* xrow = a.xln + bs * D;
+    const long long u0 = tile * PT;
+    const int np = (int)min((long long)PT, nnodes - u0);
     __syncthreads();
+    if (tid < PT) {
+      const bool ok = tid < np;
+      rbs[tid] = ok ? a.node_bs[u0 + tid] : 0;
+      rL[tid] = ok ? (int)a.node_L[u0 + tid] : 0;
+      rm[tid] = ok ? a.node_m[u0 + tid] : 0.f;
+    }
     // S1: z_ tile
     for (int i = tid; i < PT * D; i += NT) {
       const int pl = i / D, d = i - pl * D;
-      Zt[pl * Dp + d] = (pl < np) ? a.Zm[(((long long)b * P + p0 + pl) * S + s) * D + d] : 0.f;
+      Zt[pl * Dp + d] = (pl < np) ? a.Zm[(u0 + pl) * D + d] : 0.f;
     }
     for (int i = tid; i < D; i += NT) dxs[i] = 0.f;
     __syncthreads();
@@ -188,9 +288,9 @@ __global__ void __launch_bounds__(NT) bwd_dense_kernel(const BwdArgs a) {
     tile_gemm(Zt, Dp, a.p.Wz, a.p.bz, D, D, [&](int pl, int n, float v) {
       float u = 0.f;
       if (pl < np) {
-        const int L = a.anc[(((long long)b * P + p0 + pl) * S) + s];
-        const float z = __fadd_rn(v, __fmul_rn(std_z, bwd_eps(a, 3, b, s, L, n)));
-        u = z + xrow[n];
+        const int bs = rbs[pl];
+        const float z = __fadd_rn(v, __fmul_rn(std_z, bwd_eps(a, 3, bs / S, bs % S, rL[pl], n)));
+        u = z + a.xln[(long long)bs * D + n];
       }
       Ut[pl * Dp + n] = u;
     });
@@ -246,7 +346,7 @@ __global__ void __launch_bounds__(NT) bwd_dense_kernel(const BwdArgs a) {
 #pragma unroll
           for (int k = 0; k < KD; ++k) { const int d = lane + 32 * k; if (d < D) part = fmaf(r[k], __ldg(a.p.Wo + (long long)d * Fy + f), part); }
           const float pr = warp_sum(part);
-          const float dpred = (pr - a.y[bs * Fy + f]) * c_obs;
+          const float dpred = (pr - a.y[(long long)rbs[pl] * Fy + f]) * (c_obs * rm[pl]);   // m final particles share this node
 #pragma unroll
           for (int k = 0; k < KD; ++k) {
             const int d = lane + 32 * k;
@@ -307,16 +407,26 @@ __global__ void __launch_bounds__(NT) bwd_dense_kernel(const BwdArgs a) {
         if (d < D) {
           const float du = (pl < np) ? rstd * (duh[k] - m1 - uh[k] * m2) : 0.f;
           dOt[pl * Dp + d] = du;
-          if (pl < np) { atomicAdd(&g_l1g[d], dov[k] * uh[k]); atomicAdd(&g_l1b[d], dov[k]); atomicAdd(&dxs[d], du); }
+          if (pl < np) { atomicAdd(&g_l1g[d], dov[k] * uh[k]); atomicAdd(&g_l1b[d], dov[k]); }
         }
       }
     }
     __syncthreads();
-    // S12: dbz, d xln (sum over the tile's particles), dWz ; S13: dz_ = du Wz^T
-    for (int d = tid; d < D; d += NT) { g_bz[d] += dxs[d]; atomicAdd(a.dxln_sum + bs * D + d, dxs[d]); }
+    // S12: dbz, d xln (segmented sum over the tile's rows: rows of one (b,s) are contiguous), dWz ; S13: dz_ = du Wz^T
+    for (int d = tid; d < D; d += NT) {
+      float tot = 0.f, run = 0.f;
+      int cur = rbs[0];
+      for (int pl = 0; pl < np; ++pl) {
+        if (rbs[pl] != cur) { atomicAdd(a.dxln_sum + (long long)cur * D + d, run); run = 0.f; cur = rbs[pl]; }
+        const float du = dOt[pl * Dp + d];
+        run += du; tot += du;
+      }
+      atomicAdd(a.dxln_sum + (long long)cur * D + d, run);
+      g_bz[d] += tot;
+    }
     tile_outer_accum(Zt, Dp, dOt, Dp, D, D, rep + a.lay.Wz);
     tile_gemm(dOt, Dp, a.WzT, nullptr, D, D, [&](int pl, int n, float v) {
-      if (pl < np) a.dZm[(((long long)b * P + p0 + pl) * S + s) * D + n] = v;
+      if (pl < np) a.dZm[(u0 + pl) * D + n] = v;
     });
   }
   __syncthreads();
@@ -329,88 +439,91 @@ __global__ void __launch_bounds__(NT) bwd_dense_kernel(const BwdArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------
-// attention backward: one CTA per (b, group of PPC paths); warp per row; dk/dv summed over the group in smem
+// attention backward: BWD_G CTAs per sequence share its nodes (strided, so that long and short rows mix);
+// warp per node; dk/dv summed over the CTA's nodes in shared memory, then added to the (B,S,D) row sums
 // ------------------------------------------------------------------------------------------
-constexpr int BWD_PPC = 16;
+constexpr int BWD_G = 8;        // CTAs per sequence
+constexpr int BWD_ANT = 512;    // threads per CTA
 
 template <int KD>
-__global__ void __launch_bounds__(256) bwd_attn_bwd_kernel(const BwdArgs a) {
+__global__ void __launch_bounds__(BWD_ANT) bwd_attn_bwd_kernel(const BwdArgs a) {
   extern __shared__ float sm[];
-  const int D = a.D, S = a.S, P = a.P;
-  float* dKs = sm;                 // S*D: sum over the group's paths of dL/dk_tau (attention + direct noise term)
+  const int D = a.D, S = a.S;
+  float* dKs = sm;                 // S*D: sum over the CTA's nodes of dL/dk_tau (attention + direct noise term)
   float* dVs = dKs + S * D;
   float* dKX = dVs + S * D;        // direct terms only, with the sign of d/d kx
   float* dVX = dKX + S * D;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int groups = (P + BWD_PPC - 1) / BWD_PPC;
-  const int b = blockIdx.x / groups, g = blockIdx.x % groups;
-  const int p0 = g * BWD_PPC, np = min(BWD_PPC, P - p0);
+  constexpr int NWA = BWD_ANT / 32;
+  const int b = blockIdx.x / BWD_G, g = blockIdx.x % BWD_G;
   const float std_q = expf(0.5f * a.p.logvar_q[0]);
   const float sqrt_d = sqrtf((float)D);
   const float c_k = expf(-a.p.logvar_k[0]) * a.inv_n, c_v = expf(-a.p.logvar_v[0]) * a.inv_n;
-  for (int i = tid; i < 4 * S * D; i += 256) sm[i] = 0.f;
+  for (int i = tid; i < 4 * S * D; i += BWD_ANT) sm[i] = 0.f;
   __syncthreads();
-  for (int pi = 0; pi < np; ++pi) {
-    const long long bp = (long long)b * P + p0 + pi;
+  const long long u_begin = a.node_off[(long long)b * S], u_end = a.node_off[(long long)(b + 1) * S];
+  for (long long u = u_begin + g + (long long)wid * BWD_G; u < u_end; u += (long long)BWD_G * NWA) {
+    const int bs = a.node_bs[u];
+    const int s = bs % S;
+    const long long bp = (long long)b * a.P + a.node_p[u];
+    const int L = a.node_L[u];
+    const float mult = a.node_m[u];
     const float* Kp = a.K + bp * S * D;
     const float* Vp = a.V + bp * S * D;
-    for (int s = wid; s < S; s += 8) {
-      const long long row = bp * S + s;
-      const int L = a.anc[row];
-      const int s_lo = (a.attn_window >= 0 && s > a.attn_window) ? s - a.attn_window : 0;
-      float q[KD], dz[KD], dq[KD], part0 = 0.f;
+    const int s_lo = (a.attn_window >= 0 && s > a.attn_window) ? s - a.attn_window : 0;
+    float q[KD], dz[KD], dq[KD], part0 = 0.f;
+#pragma unroll
+    for (int k = 0; k < KD; ++k) {
+      const int d = lane + 32 * k;
+      const bool ok = d < D;
+      q[k] = ok ? __fadd_rn(a.q_[(long long)bs * D + d], __fmul_rn(std_q, bwd_eps(a, 1, b, s, L, d))) : 0.f;
+      dz[k] = ok ? a.dZm[u * D + d] : 0.f;
+      const float zz = ok ? a.Zm[u * D + d] : 0.f;
+      part0 = fmaf(dz[k], zz, part0);
+      dq[k] = 0.f;
+    }
+    const float delta = warp_sum(part0);     // sum_tau a_tau (dz . v_tau) = dz . z_
+    const float m = a.stat[u * 2], l = a.stat[u * 2 + 1];
+    for (int t = s_lo; t <= s; ++t) {
+      float pk = 0.f, pv = 0.f, kr[KD], vr[KD];
 #pragma unroll
       for (int k = 0; k < KD; ++k) {
         const int d = lane + 32 * k;
-        const bool ok = d < D;
-        q[k] = ok ? __fadd_rn(a.q_[((long long)b * S + s) * D + d], __fmul_rn(std_q, bwd_eps(a, 1, b, s, L, d))) : 0.f;
-        dz[k] = ok ? a.dZm[row * D + d] : 0.f;
-        const float zz = ok ? a.Zm[row * D + d] : 0.f;
-        part0 = fmaf(dz[k], zz, part0);
-        dq[k] = 0.f;
+        kr[k] = (d < D) ? Kp[(long long)t * D + d] : 0.f;
+        vr[k] = (d < D) ? Vp[(long long)t * D + d] : 0.f;
+        pk = fmaf(q[k], kr[k], pk);
+        pv = fmaf(dz[k], vr[k], pv);
       }
-      const float delta = warp_sum(part0);     // sum_tau a_tau (dz . v_tau) = dz . z_
-      const float m = a.stat[row * 2], l = a.stat[row * 2 + 1];
-      for (int t = s_lo; t <= s; ++t) {
-        float pk = 0.f, pv = 0.f, kr[KD], vr[KD];
-#pragma unroll
-        for (int k = 0; k < KD; ++k) {
-          const int d = lane + 32 * k;
-          kr[k] = (d < D) ? Kp[(long long)t * D + d] : 0.f;
-          vr[k] = (d < D) ? Vp[(long long)t * D + d] : 0.f;
-          pk = fmaf(q[k], kr[k], pk);
-          pv = fmaf(dz[k], vr[k], pv);
-        }
-        const float sc = warp_sum(pk) / sqrt_d;
-        const float dA = warp_sum(pv);
-        const float at = expf(sc - m) / l;
-        const float dS = at * (dA - delta) / sqrt_d;
-#pragma unroll
-        for (int k = 0; k < KD; ++k) {
-          const int d = lane + 32 * k;
-          if (d < D) {
-            dq[k] = fmaf(dS, kr[k], dq[k]);
-            atomicAdd(&dKs[t * D + d], dS * q[k]);
-            atomicAdd(&dVs[t * D + d], at * dz[k]);
-          }
-        }
-      }
+      const float sc = warp_sum(pk) / sqrt_d;
+      const float dA = warp_sum(pv);
+      const float at = expf(sc - m) / l;
+      const float dS = at * (dA - delta) / sqrt_d;
 #pragma unroll
       for (int k = 0; k < KD; ++k) {
         const int d = lane + 32 * k;
-        if (d < D) atomicAdd(a.dq_sum + ((long long)b * S + s) * D + d, dq[k]);
+        if (d < D) {
+          dq[k] = fmaf(dS, kr[k], dq[k]);
+          atomicAdd(&dKs[t * D + d], dS * q[k]);
+          atomicAdd(&dVs[t * D + d], at * dz[k]);
+        }
       }
     }
-    // direct terms of the loss on the resampled K/V noises: 1/2 ||K - kx||^2 / sigma_k^2 (same for V)
-    for (int i = tid; i < S * D; i += 256) {
-      const float tk = c_k * (Kp[i] - a.kx[(long long)b * S * D + i]);
-      const float tv = c_v * (Vp[i] - a.vx[(long long)b * S * D + i]);
-      atomicAdd(&dKs[i], tk); atomicAdd(&dVs[i], tv);
-      atomicAdd(&dKX[i], -tk); atomicAdd(&dVX[i], -tv);
+    // direct terms of the loss on the resampled K/V noises of this node's own row: 1/2 ||K - kx||^2 / sigma_k^2
+    // (same for V), once per final particle that descends from the node
+#pragma unroll
+    for (int k = 0; k < KD; ++k) {
+      const int d = lane + 32 * k;
+      if (d < D) {
+        atomicAdd(a.dq_sum + (long long)bs * D + d, dq[k]);
+        const float tk = mult * c_k * (Kp[(long long)s * D + d] - a.kx[(long long)bs * D + d]);
+        const float tv = mult * c_v * (Vp[(long long)s * D + d] - a.vx[(long long)bs * D + d]);
+        atomicAdd(&dKs[s * D + d], tk); atomicAdd(&dVs[s * D + d], tv);
+        atomicAdd(&dKX[s * D + d], -tk); atomicAdd(&dVX[s * D + d], -tv);
+      }
     }
   }
   __syncthreads();
-  for (int i = tid; i < S * D; i += 256) {
+  for (int i = tid; i < S * D; i += BWD_ANT) {
     const long long o = (long long)b * S * D + i;
     atomicAdd(a.dk_sum + o, dKs[i]); atomicAdd(a.dv_sum + o, dVs[i]);
     atomicAdd(a.dkx_sum + o, dKX[i]); atomicAdd(a.dvx_sum + o, dVX[i]);

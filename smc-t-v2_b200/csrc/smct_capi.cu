@@ -337,7 +337,7 @@ int forward_fused(const smct_shape& s, const smct_params& pr, const smct_io& io,
       const char* e1 = getenv("SMCT_PF_PRO");
       const char* e2 = getenv("SMCT_PF_DIST");
       pf_pro = e1 ? atoi(e1) : 0;
-      pf_dist = e2 ? atoi(e2) : 0;
+      pf_dist = e2 ? atoi(e2) : 4;   // measured on B200 (C4, one wave): 69.8 ms without, 64.4 ms with distance 4
     }
     a.pf_pro = pf_pro; a.pf_dist = pf_dist;
   }
@@ -396,6 +396,8 @@ int check_backward_shape(const smct_shape& s) {
     return fail(SMCT_ERR_UNSUPPORTED, "backward supports: gaussian weights, 1 head, full model, scalar log-variances, noise_z_mode pyc");
   if (s.D > 128) return fail(SMCT_ERR_UNSUPPORTED, "backward: d_model %d > 128", s.D);
   if ((long long)s.S * s.D > 12800) return fail(SMCT_ERR_UNSUPPORTED, "backward: S*d_model %lld > 12800", (long long)s.S * s.D);
+  if (s.P > 12288) return fail(SMCT_ERR_UNSUPPORTED, "backward: particles %d > 12288", s.P);
+  if ((long long)s.B * s.P * s.S >= (1LL << 31)) return fail(SMCT_ERR_UNSUPPORTED, "backward: B*P*S %lld >= 2^31 (run the batch in chunks)", (long long)s.B * s.P * s.S);
   return SMCT_OK;
 }
 
@@ -406,6 +408,8 @@ size_t backward_ws(const smct_shape& s) {
   n += 5 * align_up(BSD * 4);                                   // X, xln, q_, kx, vx
   n += align_up((size_t)s.D * s.D * 4) + 2 * align_up((size_t)s.D * s.dff * 4);   // transposed weights
   n += align_up(BPS * 2);                                       // anc
+  n += 2 * align_up(((size_t)s.B * s.S + 1) * 4);               // node_cnt, node_off
+  n += 2 * align_up(BPS * 4) + 2 * align_up(BPS * 2);           // node_bs, node_m, node_p, node_L
   n += 2 * align_up(BPS * s.D * 4) + align_up(BPS * 2 * 4);     // Zm, dZm, stat
   n += 6 * align_up(BSD * 4);                                   // per-row sums
   n += align_up((size_t)BWD_NREP * l.total * 4) + align_up((size_t)l.total * 4);
@@ -415,7 +419,7 @@ size_t backward_ws(const smct_shape& s) {
 template <int KD>
 int launch_backward_t(const smct::BwdArgs& a, cudaStream_t st) {
   const int D = a.D, dff = a.dff;
-  const long long nrows = (long long)a.B * a.P * a.S;
+  const long long nrows = (long long)a.B * a.P * a.S;   // upper bound of the node count (known on the device only)
   smct::bwd_attn_fwd_kernel<KD><<<(int)std::min<long long>((nrows + 7) / 8, 148LL * 64), 256, 0, st>>>(a);
   SMCT_LAUNCH_CHECK("bwd_attn_fwd_kernel");
   const size_t smem_d = ((size_t)5 * smct::PT * (D + 1) + 2 * smct::PT * (dff + 1) + smct::PT + 7 * D + dff + D * a.Fy) * sizeof(float);
@@ -426,12 +430,11 @@ int launch_backward_t(const smct::BwdArgs& a, cudaStream_t st) {
     SMCT_CUDA(cudaFuncSetAttribute(smct::bwd_attn_bwd_kernel<KD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 205 * 1024));
     attr_set = true;
   }
-  const long long ntiles = (long long)a.B * a.S * ((a.P + smct::PT - 1) / smct::PT);
+  const long long ntiles = (nrows + smct::PT - 1) / smct::PT;
   smct::bwd_dense_kernel<KD><<<(int)std::min<long long>(ntiles, a.nrep), smct::NT, smem_d, st>>>(a);
   SMCT_LAUNCH_CHECK("bwd_dense_kernel");
   const size_t smem_a = (size_t)4 * a.S * D * sizeof(float);
-  const int groups = (a.P + smct::BWD_PPC - 1) / smct::BWD_PPC;
-  smct::bwd_attn_bwd_kernel<KD><<<a.B * groups, 256, smem_a, st>>>(a);
+  smct::bwd_attn_bwd_kernel<KD><<<a.B * smct::BWD_G, smct::BWD_ANT, smem_a, st>>>(a);
   SMCT_LAUNCH_CHECK("bwd_attn_bwd_kernel");
   return SMCT_OK;
 }
@@ -703,6 +706,12 @@ int smct_backward(const smct_shape* shape, const smct_params* params, const smct
   float* kx = c.take<float>(BSD); float* vx = c.take<float>(BSD);
   float* WzT = c.take<float>((size_t)D * D); float* W1T = c.take<float>((size_t)D * s.dff); float* W2T = c.take<float>((size_t)D * s.dff);
   unsigned short* anc = c.take<unsigned short>(BPS);
+  int* node_cnt = c.take<int>((size_t)B * S + 1);
+  int* node_off = c.take<int>((size_t)B * S + 1);
+  int* node_bs = c.take<int>(BPS);
+  float* node_m = c.take<float>(BPS);
+  unsigned short* node_p = c.take<unsigned short>(BPS);
+  unsigned short* node_L = c.take<unsigned short>(BPS);
   float* Zm = c.take<float>(BPS * D); float* dZm = c.take<float>(BPS * D); float* stat = c.take<float>(BPS * 2);
   float* sums = c.take<float>(6 * BSD);   // contiguous: one memset
   float* rep = c.take<float>((size_t)BWD_NREP * lay.total);
@@ -731,6 +740,21 @@ int smct_backward(const smct_shape* shape, const smct_params* params, const smct
   smct::anc_trace_kernel<<<(int)std::min<long long>(((long long)B * P + 255) / 256, 148 * 8), 256, 0, st>>>(
       B, P, S, s.len_resampling, io->i_out, anc);
   SMCT_LAUNCH_CHECK("anc_trace_kernel");
+  {  // unique (slot, ancestor) nodes of the final genealogy: count, scan, fill
+    const size_t smem_n = (size_t)2 * P * sizeof(int);
+    static bool node_attr = false;
+    if (!node_attr) {
+      SMCT_CUDA(cudaFuncSetAttribute(smct::node_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 12288 * (int)sizeof(int)));
+      SMCT_CUDA(cudaFuncSetAttribute(smct::node_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 12288 * (int)sizeof(int)));
+      node_attr = true;
+    }
+    smct::node_count_kernel<<<B * S, 256, smem_n, st>>>(P, anc, node_cnt);
+    SMCT_LAUNCH_CHECK("node_count_kernel");
+    smct::node_scan_kernel<<<1, 1024, 0, st>>>(B * S, node_cnt, node_off);
+    SMCT_LAUNCH_CHECK("node_scan_kernel");
+    smct::node_fill_kernel<<<B * S, 256, smem_n, st>>>(P, anc, node_off, node_bs, node_p, node_L, node_m);
+    SMCT_LAUNCH_CHECK("node_fill_kernel");
+  }
 
   smct::BwdArgs a;
   memset(&a, 0, sizeof(a));
@@ -740,7 +764,7 @@ int smct_backward(const smct_shape* shape, const smct_params* params, const smct
   a.b_global0 = s.b_global0; a.seed = io->seed;
   a.x_in = io->x_in; a.X = X; a.xln = xln; a.q_ = q_; a.kx = kx; a.vx = vx;
   a.y = (const float*)io->y; a.eps = io->eps; a.p = *params; a.WzT = WzT; a.W1T = W1T; a.W2T = W2T;
-  a.K = io->K; a.V = io->V; a.i_out = io->i_out; a.anc = anc; a.Zm = Zm; a.dZm = dZm; a.stat = stat;
+  a.K = io->K; a.V = io->V; a.i_out = io->i_out; a.anc = anc; a.node_off = node_off; a.node_bs = node_bs; a.node_p = node_p; a.node_L = node_L; a.node_m = node_m; a.Zm = Zm; a.dZm = dZm; a.stat = stat;
   a.dq_sum = dq_sum; a.dk_sum = dk_sum; a.dv_sum = dv_sum; a.dxln_sum = dxln_sum; a.dkx_sum = dkx_sum; a.dvx_sum = dvx_sum;
   a.rep = rep; a.nrep = BWD_NREP; a.lay = lay;
   int rc;
