@@ -297,6 +297,8 @@ int forward_fused(const smct_shape& s, const smct_params& pr, const smct_io& io,
   float* Kp = c.take<float>(BSPD);
   float* Vp = c.take<float>(BSPD);
   float* Rp = c.take<float>(BSPD);
+  unsigned char* Ks = c.take<unsigned char>(BSPD * 4);   // fp16 (h,m) split copies of the K/V rows (attention operands)
+  unsigned char* Vs = c.take<unsigned char>(BSPD * 4);
   unsigned short* A0 = c.take<unsigned short>((size_t)B * P * Sa);
   unsigned short* A1 = c.take<unsigned short>((size_t)B * P * Sa);
   unsigned short* pos = c.take<unsigned short>((size_t)B * P);
@@ -305,7 +307,8 @@ int forward_fused(const smct_shape& s, const smct_params& pr, const smct_io& io,
 
   if (io.loss_sums) SMCT_CUDA(cudaMemsetAsync(io.loss_sums, 0, 8 * sizeof(double), st));
   if (use_tc) {
-    smct::tc_weight_prep_kernel<<<1, 1024, 0, st>>>(pr.Wz, pr.W1, pr.W2, pr.b1, pr.ln1_g, pr.ln1_b, smct::FF, wtc);
+    smct::TcAttnPrep ap{pr.Wq, pr.bq, pr.Wk, pr.bk, pr.Wv, pr.bv, pr.logvar_q, pr.logvar_k, pr.logvar_v, s.logvar_dim};
+    smct::tc_weight_prep_kernel<<<1, 1024, 0, st>>>(pr.Wz, pr.W1, pr.W2, pr.b1, pr.ln1_g, pr.ln1_b, smct::FF, wtc, ap);
     SMCT_LAUNCH_CHECK("tc_weight_prep_kernel");
   }
 
@@ -327,7 +330,7 @@ int forward_fused(const smct_shape& s, const smct_params& pr, const smct_io& io,
   a.xln = xln; a.q_ = q_; a.k_ = k_; a.v_ = v_;
   a.y = (const float*)io.y; a.eps = io.eps; a.u = io.u; a.i_forced = io.i_forced;
   a.p = pr;
-  a.Kp = Kp; a.Vp = Vp; a.Rp = Rp; a.A0 = A0; a.A1 = A1; a.pos_out = pos; a.aflag = aflag;
+  a.Kp = Kp; a.Vp = Vp; a.Rp = Rp; a.Ks = Ks; a.Vs = Vs; a.A0 = A0; a.A1 = A1; a.pos_out = pos; a.aflag = aflag;
   a.pred = io.pred; a.w = io.w; a.logw = io.logw; a.noise_q = io.noise_q; a.noise_z = io.noise_z;
   a.i_out = io.i_out; a.loss_sums = io.loss_sums;
   a.wtc = wtc;

@@ -43,6 +43,7 @@ struct FusedArgs {
   smct_params p;
   const unsigned char* wtc;          // bf16 (h,m) weight blocks in the tcgen05 operand layout (tensor-core variant)
   float *Kp, *Vp, *Rp;               // (B,S,P,64) slot-major physical rows
+  unsigned char *Ks, *Vs;            // (B,S,P,256 B) fp16 (h,m) split copies of the K/V rows (tensor-core variant)
   unsigned short *A0, *A1;           // (B,P,Sa) ancestry rows, ping-pong
   unsigned short* pos_out;           // (B,P)  final position of each logical particle
   int* aflag;                        // (B)    which ancestry buffer is final
@@ -622,7 +623,7 @@ inline size_t fused_forward_ws(const smct_shape& s) {
   const size_t Sa = (size_t)(s.S + 7) / 8 * 8;
   size_t n = 0;
   n += 6 * fused_align((size_t)s.B * s.S * FD * sizeof(float));
-  n += 3 * fused_align((size_t)s.B * s.S * s.P * FD * sizeof(float));
+  n += 5 * fused_align((size_t)s.B * s.S * s.P * FD * sizeof(float));   // Kp, Vp, Rp + split copies of K, V
   n += 2 * fused_align((size_t)s.B * s.P * Sa * sizeof(unsigned short));
   n += fused_align((size_t)s.B * s.P * sizeof(unsigned short));
   n += fused_align((size_t)s.B * sizeof(int));

@@ -13,6 +13,7 @@
 #pragma once
 #include "smct_fused.cuh"
 #include "smct_tc.cuh"
+#include "smct_fused_attn.cuh"
 
 namespace smct {
 
@@ -27,6 +28,7 @@ struct FusedTcSmem {
   __align__(128) unsigned char Ob[2 * tc::A_PART_BYTES];   // A operand: o = LN1(z + x) (h,m)
   __align__(128) unsigned char Wzb[2 * tc::B_PART_BYTES];  // B operand: Wz (h,m)
   __align__(128) unsigned char Wc[2][4 * tc::B_PART_BYTES];// B operands: W1 chunk (h,m) + W2 chunk (h,m), double-buffered
+  __align__(8) uint2 cdesc[FNT / 32][16];             // per-warp column descriptors of the attention groups
   __align__(8) uint64_t mbar;
   uint32_t tmem_slot;
 };
@@ -109,7 +111,9 @@ __global__ void __launch_bounds__(FNT, 1) fused_tc_forward_kernel(const FusedArg
   float* const Kb = a.Kp + (long long)b * S * P * FD;
   float* const Vb = a.Vp + (long long)b * S * P * FD;
   float* const Rb = a.Rp + (long long)b * S * P * FD;
-  const int pl = tid >> 2, l4 = tid & 3;          // attention: particle-in-tile, lane-in-particle
+  unsigned char* const Ksb = a.Ks + ((size_t)b * S * P << 8);
+  unsigned char* const Vsb = a.Vs + ((size_t)b * S * P << 8);
+  const int pl = tid >> 2, l4 = tid & 3;          // noise / output stages: particle-in-tile, lane-in-particle
   const int er = (wid & 3) * 32 + lane;           // epilogue: row of the tile (= TMEM lane)
   const int ecq = wid >> 2;                       // epilogue: column quarter, cols [16*ecq, 16*ecq+16)
   const uint32_t tlane = ((uint32_t)((wid & 3) * 32)) << 16;
@@ -158,7 +162,7 @@ __global__ void __launch_bounds__(FNT, 1) fused_tc_forward_kernel(const FusedArg
       copy_block_async(sm.Wc[0], a.wtc + 2 * tc::B_PART_BYTES, 4 * tc::B_PART_BYTES);
       cp_async_commit();
 
-      // =========================== phase A: noise, slot-t rows, attention ===========================
+      // =========================== phase A1: noise, slot-t rows (fp32 + fp16 split), q tile ===========================
       {
         const int q = q0 + pl;
         const bool act = pl < np;
@@ -167,19 +171,10 @@ __global__ void __launch_bounds__(FNT, 1) fused_tc_forward_kernel(const FusedArg
         const unsigned long long gbp = (unsigned long long)(a.b_global0 + b) * (unsigned long long)P + L;
         const long long lrow = ((bP + L) * S + t) * FD;
         const uint32_t prow = (uint32_t)(t * P + qc) * FD;
-        const unsigned short* Arow = Acur + (long long)qc * Sa;
-        const int nfull = (t - s_lo) / FSB;   // blocks made only of slots < t
-        {  // L2 prefetch of the first history blocks: they travel while the noise is generated
-          const int npro = min(a.pf_pro, nfull);
-          for (int pb = 0; pb < npro; ++pb) {
-            const int sp = s_lo + pb * FSB + (l4 >> 1);
-            prefetch_rows(Kb, Vb, sp, (int)Arow[sp], P, l4);
-          }
-        }
-        float4 qv[4];
+        float ko[16], vo[16];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const int c = l4 + 4 * i, d0 = 4 * c;
+          const int c = 4 * l4 + i, d0 = 4 * c;          // lane l4 owns dims [16 l4, 16 l4 + 16)
           const float4 q_0 = *reinterpret_cast<const float4*>(&sm.c.rowbuf[1][d0]);
           const float4 k_0 = *reinterpret_cast<const float4*>(&sm.c.rowbuf[2][d0]);
           const float4 v_0 = *reinterpret_cast<const float4*>(&sm.c.rowbuf[3][d0]);
@@ -201,105 +196,167 @@ __global__ void __launch_bounds__(FNT, 1) fused_tc_forward_kernel(const FusedArg
           const float kin[4] = {k_0.x, k_0.y, k_0.z, k_0.w};
           const float qin[4] = {q_0.x, q_0.y, q_0.z, q_0.w};
           const float vin[4] = {v_0.x, v_0.y, v_0.z, v_0.w};
-          float ko[4], qo[4], vo[4], nq[4];
+          float qo[4], nq[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            ko[e] = __fadd_rn(kin[e], __fmul_rn(sm.c.stdtab[0][d0 + e], ek[e]));
+            ko[4 * i + e] = __fadd_rn(kin[e], __fmul_rn(sm.c.stdtab[0][d0 + e], ek[e]));
             qo[e] = __fadd_rn(qin[e], __fmul_rn(sm.c.stdtab[1][d0 + e], eq[e]));
-            vo[e] = __fadd_rn(vin[e], __fmul_rn(sm.c.stdtab[2][d0 + e], ev[e]));
+            vo[4 * i + e] = __fadd_rn(vin[e], __fmul_rn(sm.c.stdtab[2][d0 + e], ev[e]));
             nq[e] = qo[e] - qin[e];
             loss_q = act ? fmaf(nq[e] * nq[e], sm.c.ivar[1][d0 + e], loss_q) : loss_q;
           }
-          // scores are formed in the log2 domain: q is pre-scaled by log2(e)/sqrt(d_k)
-          const float qs = 0.125f * 1.4426950408889634f;
-          qv[i] = make_float4(qo[0] * qs, qo[1] * qs, qo[2] * qs, qo[3] * qs);
+          // q tile for the MMA fragments: scaled by log2(e)/sqrt(d_k) (scores in the log2 domain) and the fp16 scale
+          const float qs = sm.hdr.s_q;
+          *reinterpret_cast<float4*>(&sm.Os[pl * FLD + d0]) = make_float4(qo[0] * qs, qo[1] * qs, qo[2] * qs, qo[3] * qs);
           if (act) {
-            *reinterpret_cast<float4*>(Kb + prow + d0) = make_float4(ko[0], ko[1], ko[2], ko[3]);
-            *reinterpret_cast<float4*>(Vb + prow + d0) = make_float4(vo[0], vo[1], vo[2], vo[3]);
+            *reinterpret_cast<float4*>(Kb + prow + d0) = make_float4(ko[4 * i], ko[4 * i + 1], ko[4 * i + 2], ko[4 * i + 3]);
+            *reinterpret_cast<float4*>(Vb + prow + d0) = make_float4(vo[4 * i], vo[4 * i + 1], vo[4 * i + 2], vo[4 * i + 3]);
             if (a.noise_q) __stcs(reinterpret_cast<float4*>(a.noise_q + lrow + d0), make_float4(nq[0], nq[1], nq[2], nq[3]));
           }
         }
-        // causal attention over the genealogy: slot s lives in physical row A[q][s] (s < t) or q (s == t)
-        float m = -INFINITY, l = 0.f;
-        float4 zacc[4];
+        if (act) {   // fp16 (h,m) split copies of the new rows in the MMA operand order (smct_fused_attn.cuh)
+          unsigned char* ksr = Ksb + ((size_t)(t * P + qc) << 8);
+          unsigned char* vsr = Vsb + ((size_t)(t * P + qc) << 8);
+          const float sk = sm.hdr.s_k, sv = sm.hdr.s_v;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) zacc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        int s = s_lo;
-        const int pfd = a.pf_dist;
-        int rpf = (pfd > 0 && pfd < nfull) ? (int)Arow[s_lo + pfd * FSB + (l4 >> 1)] : 0;
-        int rn[FSB];
+          for (int half = 0; half < 2; ++half) {
+            float x[8];
+            uint4 h, m;
 #pragma unroll
-        for (int j = 0; j < FSB; ++j) rn[j] = (nfull > 0) ? (int)Arow[s_lo + j] : 0;
-        for (int blk = 0; blk < nfull; ++blk, s += FSB) {
-          uint32_t off[FSB];
+            for (int e = 0; e < 8; ++e) x[e] = ko[8 * half + e] * sk;
+            attn::split8(x, h, m);
+            *reinterpret_cast<uint4*>(ksr + 16 * (half * 4 + l4)) = h;
+            *reinterpret_cast<uint4*>(ksr + 16 * (8 + half * 4 + l4)) = m;
 #pragma unroll
-          for (int j = 0; j < FSB; ++j) off[j] = (uint32_t)((s + j) * P + rn[j]) * FD + 4 * l4;
-          if (blk + 1 < nfull) {
-#pragma unroll
-            for (int j = 0; j < FSB; ++j) rn[j] = (int)Arow[s + FSB + j];
+            for (int e = 0; e < 8; ++e) x[e] = vo[8 * half + e] * sv;
+            attn::split8(x, h, m);
+            *reinterpret_cast<uint4*>(vsr + 32 * l4 + 16 * half) = h;
+            *reinterpret_cast<uint4*>(vsr + 128 + 32 * l4 + 16 * half) = m;
           }
-          if (pfd > 0 && blk + pfd < nfull) {
-            prefetch_rows(Kb, Vb, s + pfd * FSB + (l4 >> 1), rpf, P, l4);
-            if (blk + pfd + 1 < nfull) rpf = (int)Arow[s + (pfd + 1) * FSB + (l4 >> 1)];
-          }
-          float sc[FSB];
-          float4 vr[FSB][4];
+        }
+      }
+      __syncthreads();   // q tile complete; the slot-t rows of this tile are visible to the whole CTA
+
+      // =========================== phase A2: attention over the genealogy (warp-level MMAs) ===========================
+      {
+        const int grp = wid & 7, hsel = wid >> 3;    // 16 particles per group; the two warps of a group split the slot blocks
+        const int r = lane >> 2, c = lane & 3;
+        attn::State st;
+        uint4* Qf = reinterpret_cast<uint4*>(sm.Ob) + grp * 256;   // this group's Q fragments (Ob is free until the LN1 epilogue)
 #pragma unroll
-          for (int j = 0; j < FSB; ++j) {
-            float4 kr[4];
+        for (int jj = 0; jj < 2; ++jj) {   // the two warps of a group split the four k-steps
+          const int j = 2 * hsel + jj;
+          const float4 x0 = *reinterpret_cast<const float4*>(&sm.Os[(16 * grp + r) * FLD + 16 * c + 4 * j]);
+          const float4 x1 = *reinterpret_cast<const float4*>(&sm.Os[(16 * grp + r + 8) * FLD + 16 * c + 4 * j]);
+          uint4 qh, qm;
+          attn::split2(attn::sat16(x0.x), attn::sat16(x0.y), qh.x, qm.x);
+          attn::split2(attn::sat16(x1.x), attn::sat16(x1.y), qh.y, qm.y);
+          attn::split2(attn::sat16(x0.z), attn::sat16(x0.w), qh.z, qm.z);
+          attn::split2(attn::sat16(x1.z), attn::sat16(x1.w), qh.w, qm.w);
+          Qf[j * 32 + lane] = qh;
+          Qf[(4 + j) * 32 + lane] = qm;
+        }
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              kr[i] = *reinterpret_cast<const float4*>(Kb + off[j] + 16 * i);
-              vr[j][i] = *reinterpret_cast<const float4*>(Vb + off[j] + 16 * i);
+        for (int i = 0; i < 8; ++i) st.Z[i][0] = st.Z[i][1] = st.Z[i][2] = st.Z[i][3] = 0.f;
+        st.m0 = st.m1 = -INFINITY; st.l0 = st.l1 = 0.f;
+        __syncthreads();   // Q fragments complete; Os may now be overwritten by the partial results
+        const int l15 = lane & 15, hsl = lane >> 4;
+        const int myq = min(q0 + 16 * grp + l15, P - 1);
+        const unsigned short* Arow = Acur + (long long)myq * Sa;
+        uint2* cd = sm.cdesc[wid];
+        const float inv_qk = sm.hdr.inv_qk;
+        const uint32_t ltmask = (1u << lane) - 1u;
+        int ncols = 0;
+        // column builder: the two half-warps look at two consecutive slots per pass (lane & 15 = particle of the group);
+        // a particle opens a column when its ancestor differs from its left neighbour's (the ancestry is monotone)
+        for (int blk = (s_lo >> 3) + (((s_lo >> 3) & 1) != hsel ? 1 : 0); blk <= (t >> 3); blk += 2) {
+          uint4 av = make_uint4(0u, 0u, 0u, 0u);
+          if (8 * blk < t) av = *reinterpret_cast<const uint4*>(Arow + 8 * blk);
+#pragma unroll 1
+          for (int pass = 0; pass < 4; ++pass) {
+            const int s = 8 * blk + 2 * pass + hsl;
+            const uint32_t w = pass < 2 ? (pass == 0 ? av.x : av.y) : (pass == 2 ? av.z : av.w);
+            int aval = hsl ? (int)(w >> 16) : (int)(w & 0xFFFFu);
+            if (s == t) aval = myq;                       // the current slot: the particle's own row
+            const int prev = __shfl_up_sync(SMCT_FULL_MASK, aval, 1);
+            const bool head = (s >= s_lo) && (s <= t) && (l15 == 0 || aval != prev);
+            const uint32_t hb = __ballot_sync(SMCT_FULL_MASK, head);
+            uint32_t pend = hb;
+            while (pend) {
+              uint32_t take = pend;
+              if (ncols + __popc(take) > 16) {
+                const uint32_t low = pend & 0xFFFFu;
+                if (low != 0u && ncols + __popc(low) <= 16) {
+                  take = low;
+                } else if (ncols > 0) {
+                  attn::process_group(st, cd, ncols, Qf, Ksb, Vsb, P, inv_qk, lane);
+                  ncols = 0;
+                  continue;
+                } else {
+                  take = low ? low : pend;                // an empty group always has room for one slot
+                }
+              }
+              if (head && ((take >> lane) & 1u)) {
+                const int col = ncols + __popc(take & ltmask);
+                const uint32_t above = (hsl ? (hb >> 16) : (hb & 0xFFFFu)) >> (l15 + 1);
+                const int hi = above ? (l15 + __ffs((int)above)) : 16;
+                cd[col] = make_uint2(((uint32_t)s << 16) | (uint32_t)aval, ((uint32_t)hi << 8) | (uint32_t)l15);
+              }
+              __syncwarp();
+              ncols += __popc(take);
+              pend &= ~take;
             }
-            float part = dot4(qv[1], kr[1], dot4(qv[0], kr[0], 0.f)) + dot4(qv[3], kr[3], dot4(qv[2], kr[2], 0.f));
-            part += __shfl_xor_sync(SMCT_FULL_MASK, part, 1);
-            part += __shfl_xor_sync(SMCT_FULL_MASK, part, 2);
-            sc[j] = part;
           }
-          softmax_block(sc, vr, m, l, zacc);
         }
-        {  // tail block: the remaining slots < t (fewer than FSB) and the current slot t
-          float sc[FSB];
-          float4 vr[FSB][4];
+        if (ncols > 0) attn::process_group(st, cd, ncols, Qf, Ksb, Vsb, P, inv_qk, lane);
+        // ---- merge the two halves of every group through shared memory ----
+        const int R0 = 16 * grp + r, R1 = R0 + 8;
+        if (hsel == 1) {
 #pragma unroll
-          for (int j = 0; j < FSB; ++j) {
-            const int sj = s + j;
-            const bool val = sj <= t;
-            const int sjc = val ? sj : t;
-            const int row = (sjc < t) ? (int)Arow[sjc] : qc;
-            const uint32_t off = (uint32_t)(sjc * P + row) * FD + 4 * l4;
-            float part = 0.f;
+          for (int k4 = 0; k4 < 4; ++k4) {   // dims 16c + 4 k4 .. +3 : Z[i][0] = dim 16c+i, Z[i][1] = dim 16c+8+i
+            const int i0 = (k4 & 1) * 4, e = k4 >> 1;
+            *reinterpret_cast<float4*>(&sm.Os[R0 * FLD + 16 * c + 4 * k4]) = make_float4(st.Z[i0][e], st.Z[i0 + 1][e], st.Z[i0 + 2][e], st.Z[i0 + 3][e]);
+            *reinterpret_cast<float4*>(&sm.Os[R1 * FLD + 16 * c + 4 * k4]) = make_float4(st.Z[i0][2 + e], st.Z[i0 + 1][2 + e], st.Z[i0 + 2][2 + e], st.Z[i0 + 3][2 + e]);
+          }
+          if (c == 0) { sm.psum[0][0][R0] = st.m0; sm.psum[0][1][R0] = st.l0; sm.psum[0][0][R1] = st.m1; sm.psum[0][1][R1] = st.l1; }
+        }
+        __syncthreads();
+        if (hsel == 0) {
+          const float mB0 = sm.psum[0][0][R0], lB0 = sm.psum[0][1][R0], mB1 = sm.psum[0][0][R1], lB1 = sm.psum[0][1][R1];
+          const float mt0 = fmaxf(st.m0, mB0), mt1 = fmaxf(st.m1, mB1);
+          const float cA0 = attn::ex2f(st.m0 - mt0), cB0 = attn::ex2f(mB0 - mt0);
+          const float cA1 = attn::ex2f(st.m1 - mt1), cB1 = attn::ex2f(mB1 - mt1);
+          const float il0 = sm.hdr.inv_v / fmaf(st.l0, cA0, lB0 * cB0), il1 = sm.hdr.inv_v / fmaf(st.l1, cA1, lB1 * cB1);
+          float z0[16], z1[16];
+          float rmax0 = 0.f, rmax1 = 0.f;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float4 kr = *reinterpret_cast<const float4*>(Kb + off + 16 * i);
-              vr[j][i] = *reinterpret_cast<const float4*>(Vb + off + 16 * i);
-              part = dot4(qv[i], kr, part);
+          for (int k4 = 0; k4 < 4; ++k4) {
+            const int i0 = (k4 & 1) * 4, e = k4 >> 1;
+            const float4 b0 = *reinterpret_cast<const float4*>(&sm.Os[R0 * FLD + 16 * c + 4 * k4]);
+            const float4 b1 = *reinterpret_cast<const float4*>(&sm.Os[R1 * FLD + 16 * c + 4 * k4]);
+            const float pb0[4] = {b0.x, b0.y, b0.z, b0.w}, pb1[4] = {b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              z0[4 * k4 + k] = fmaf(st.Z[i0 + k][e], cA0, pb0[k] * cB0) * il0;
+              z1[4 * k4 + k] = fmaf(st.Z[i0 + k][2 + e], cA1, pb1[k] * cB1) * il1;
+              rmax0 = fmaxf(rmax0, fabsf(z0[4 * k4 + k])); rmax1 = fmaxf(rmax1, fabsf(z1[4 * k4 + k]));
             }
-            part += __shfl_xor_sync(SMCT_FULL_MASK, part, 1);
-            part += __shfl_xor_sync(SMCT_FULL_MASK, part, 2);
-            sc[j] = val ? part : -INFINITY;
           }
-          softmax_block(sc, vr, m, l, zacc);
-        }
-        const float inv_l = act ? 1.0f / l : 0.f;
-        float rmax = 0.f;
+          rmax0 = fmaxf(rmax0, __shfl_xor_sync(SMCT_FULL_MASK, rmax0, 1)); rmax0 = fmaxf(rmax0, __shfl_xor_sync(SMCT_FULL_MASK, rmax0, 2));
+          rmax1 = fmaxf(rmax1, __shfl_xor_sync(SMCT_FULL_MASK, rmax1, 1)); rmax1 = fmaxf(rmax1, __shfl_xor_sync(SMCT_FULL_MASK, rmax1, 2));
+          const int ez0 = tc::scale_exponent(rmax0), ez1 = tc::scale_exponent(rmax1);   // exact power-of-two scales of the rows' fp16 operand
+          const float zs0 = ldexpf(1.f, ez0), zs1 = ldexpf(1.f, ez1);
+          if (c == 0) { sm.rs[R0] = ldexpf(1.f, -ez0); sm.rs[R1] = ldexpf(1.f, -ez1); }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          zacc[i] = make_float4(zacc[i].x * inv_l, zacc[i].y * inv_l, zacc[i].z * inv_l, zacc[i].w * inv_l);
-          rmax = fmaxf(rmax, fmaxf(fmaxf(fabsf(zacc[i].x), fabsf(zacc[i].y)), fmaxf(fabsf(zacc[i].z), fabsf(zacc[i].w))));
-        }
-        rmax = fmaxf(rmax, __shfl_xor_sync(SMCT_FULL_MASK, rmax, 1));
-        rmax = fmaxf(rmax, __shfl_xor_sync(SMCT_FULL_MASK, rmax, 2));
-        const int ez = tc::scale_exponent(rmax);            // exact power-of-two scale of this row's fp16 operand
-        const float zs = ldexpf(1.f, ez);
-        if (l4 == 0) sm.rs[pl] = ldexpf(1.f, -ez);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int d0 = 4 * (l4 + 4 * i);
-          *reinterpret_cast<float4*>(&sm.Os[pl * FLD + d0]) = zacc[i];
-          const float zz[4] = {zacc[i].x * zs, zacc[i].y * zs, zacc[i].z * zs, zacc[i].w * zs};
-          tc::store_a4(sm.ZH, pl, d0, zz);
+          for (int k4 = 0; k4 < 4; ++k4) {
+            const int d0 = 16 * c + 4 * k4;
+            *reinterpret_cast<float4*>(&sm.Os[R0 * FLD + d0]) = make_float4(z0[4 * k4], z0[4 * k4 + 1], z0[4 * k4 + 2], z0[4 * k4 + 3]);
+            *reinterpret_cast<float4*>(&sm.Os[R1 * FLD + d0]) = make_float4(z1[4 * k4], z1[4 * k4 + 1], z1[4 * k4 + 2], z1[4 * k4 + 3]);
+            const float zz0[4] = {z0[4 * k4] * zs0, z0[4 * k4 + 1] * zs0, z0[4 * k4 + 2] * zs0, z0[4 * k4 + 3] * zs0};
+            const float zz1[4] = {z1[4 * k4] * zs1, z1[4 * k4 + 1] * zs1, z1[4 * k4 + 2] * zs1, z1[4 * k4 + 3] * zs1};
+            tc::store_a4(sm.ZH, R0, d0, zz0);
+            tc::store_a4(sm.ZH, R1, d0, zz1);
+          }
         }
       }
       cp_async_wait_all();

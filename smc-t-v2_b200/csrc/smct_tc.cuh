@@ -177,11 +177,20 @@ struct TcHeader {
   float s_o, inv_o;               // scale of o = LN1(.) (bounded by 8 max|gamma1| + max|beta1|) and its inverse
   float s_h, inv_h;               // scale of h = relu(o W1 + b1) (bounded analytically) and its inverse
   float pad;
+  // attention operands (warp-level fp16 split MMAs): exact power-of-two scales of q (incl. log2(e)/sqrt(d_k)), k, v
+  // from analytic bounds |LN1(x) W + b| + 16 sigma, and the inverse scales of the scores and of z_
+  float s_q, s_k, s_v, inv_qk, inv_v;
+  float pad2[3];
+};
+
+struct TcAttnPrep {     // optional inputs for the attention operand scales
+  const float *Wq, *bq, *Wk, *bk, *Wv, *bv, *logvar_q, *logvar_k, *logvar_v;
+  int logvar_dim;
 };
 
 __global__ void __launch_bounds__(1024) tc_weight_prep_kernel(const float* Wz, const float* W1, const float* W2,
                                                               const float* b1, const float* ln_g, const float* ln_b,
-                                                              int dff, unsigned char* out) {
+                                                              int dff, unsigned char* out, TcAttnPrep ap = TcAttnPrep{}) {
   __shared__ float red[32];
   __shared__ float sc[8];
   const int tid = threadIdx.x;
@@ -210,6 +219,22 @@ __global__ void __launch_bounds__(1024) tc_weight_prep_kernel(const float* Wz, c
     for (int i = tid; i < 64; i += 1024) { mg = fmaxf(mg, fabsf(ln_g[i])); mbt = fmaxf(mbt, fabsf(ln_b[i])); }
   }
   m1 = bmax(m1); m2 = bmax(m2); mb1 = bmax(mb1); mg = bmax(mg); mbt = bmax(mbt); colsum = bmax(colsum);
+  float bq = 0.f, bk = 0.f, bv = 0.f;   // bounds of |q|, |k|, |v| (projection of LN1(x) plus 16 standard deviations of noise)
+  if (ap.Wq) {
+    float cq = 0.f, ck = 0.f, cv = 0.f, aq = 0.f, ak = 0.f, av = 0.f, sq = 0.f, sk = 0.f, sv = 0.f;
+    for (int j = tid; j < 64; j += 1024) {
+      float s1 = 0.f, s2 = 0.f, s3 = 0.f;
+      for (int k = 0; k < 64; ++k) { s1 += fabsf(ap.Wq[k * 64 + j]); s2 += fabsf(ap.Wk[k * 64 + j]); s3 += fabsf(ap.Wv[k * 64 + j]); }
+      cq = s1; ck = s2; cv = s3;
+      aq = fabsf(ap.bq[j]); ak = fabsf(ap.bk[j]); av = fabsf(ap.bv[j]);
+      const int li = ap.logvar_dim > 1 ? j : 0;
+      sq = expf(0.5f * ap.logvar_q[li]); sk = expf(0.5f * ap.logvar_k[li]); sv = expf(0.5f * ap.logvar_v[li]);
+    }
+    cq = bmax(cq); ck = bmax(ck); cv = bmax(cv); aq = bmax(aq); ak = bmax(ak); av = bmax(av);
+    sq = bmax(sq); sk = bmax(sk); sv = bmax(sv);
+    const float bo = 8.0f * mg + mbt;
+    bq = bo * cq + aq + 16.f * sq; bk = bo * ck + ak + 16.f * sk; bv = bo * cv + av + 16.f * sv;
+  }
   if (tid == 0) {
     const float bound_o = 8.0f * mg + mbt;                 // |LN(x)_n| <= sqrt(63) |gamma_n| + |beta_n|
     const float bound_h = bound_o * colsum + mb1;          // |relu(o W1 + b1)_j| <= ||o||_inf sum_k |W1[k][j]| + |b1_j|
@@ -220,6 +245,13 @@ __global__ void __launch_bounds__(1024) tc_weight_prep_kernel(const float* Wz, c
     h->inv_wz = ldexpf(1.f, -ez); h->inv_w1 = ldexpf(1.f, -e1); h->inv_w2 = ldexpf(1.f, -e2);
     h->s_o = ldexpf(1.f, eo); h->inv_o = ldexpf(1.f, -eo); h->s_h = ldexpf(1.f, eh); h->inv_h = ldexpf(1.f, -eh);
     h->pad = 0.f;
+    // attention operands: bound -> [2^13, 2^14] (fp16 max 65504); typical values sit 10-20x below the bound
+    const float qs = 0.125f * 1.4426950408889634f;   // log2(e) / sqrt(d_k), d_k = 64
+    const int eq = ap.Wq ? tc::scale_exponent(bq * qs) + 4 : 0, ek = ap.Wq ? tc::scale_exponent(bk) + 4 : 0,
+              ev = ap.Wq ? tc::scale_exponent(bv) + 4 : 0;
+    h->s_q = ldexpf(qs, eq); h->s_k = ldexpf(1.f, ek); h->s_v = ldexpf(1.f, ev);
+    h->inv_qk = ldexpf(1.f, -(eq + ek)); h->inv_v = ldexpf(1.f, -ev);
+    h->pad2[0] = h->pad2[1] = h->pad2[2] = 0.f;
   }
   __syncthreads();
   for (int idx = tid; idx < nblk * 4096; idx += 1024) {
