@@ -209,8 +209,13 @@ __global__ void __launch_bounds__(FNT, 1) fused_tc_forward_kernel(const FusedArg
           const float qs = sm.hdr.s_q;
           *reinterpret_cast<float4*>(&sm.Os[pl * FLD + d0]) = make_float4(qo[0] * qs, qo[1] * qs, qo[2] * qs, qo[3] * qs);
           if (act) {
+#if SMCT_X_STCS   // fp32 rows: read again only by the final pass
+            __stcs(reinterpret_cast<float4*>(Kb + prow + d0), make_float4(ko[4 * i], ko[4 * i + 1], ko[4 * i + 2], ko[4 * i + 3]));
+            __stcs(reinterpret_cast<float4*>(Vb + prow + d0), make_float4(vo[4 * i], vo[4 * i + 1], vo[4 * i + 2], vo[4 * i + 3]));
+#else
             *reinterpret_cast<float4*>(Kb + prow + d0) = make_float4(ko[4 * i], ko[4 * i + 1], ko[4 * i + 2], ko[4 * i + 3]);
             *reinterpret_cast<float4*>(Vb + prow + d0) = make_float4(vo[4 * i], vo[4 * i + 1], vo[4 * i + 2], vo[4 * i + 3]);
+#endif
             if (a.noise_q) __stcs(reinterpret_cast<float4*>(a.noise_q + lrow + d0), make_float4(nq[0], nq[1], nq[2], nq[3]));
           }
         }
@@ -267,15 +272,45 @@ __global__ void __launch_bounds__(FNT, 1) fused_tc_forward_kernel(const FusedArg
         const float inv_qk = sm.hdr.inv_qk;
         const uint32_t ltmask = (1u << lane) - 1u;
         int ncols = 0;
-        // column builder: the two half-warps look at two consecutive slots per pass (lane & 15 = particle of the group);
-        // a particle opens a column when its ancestor differs from its left neighbour's (the ancestry is monotone)
-        for (int blk = (s_lo >> 3) + (((s_lo >> 3) & 1) != hsel ? 1 : 0); blk <= (t >> 3); blk += 2) {
-          uint4 av = make_uint4(0u, 0u, 0u, 0u);
-          if (8 * blk < t) av = *reinterpret_cast<const uint4*>(Arow + 8 * blk);
+        // column builder.  Units of 4 slots alternate between the two warps of a group.  A particle opens a column when
+        // its ancestor differs from its left neighbour's (the ancestry is monotone in the position).  Old slots are
+        // usually shared by all 16 particles: a unit whose ancestry words are identical across the group adds its 4
+        // columns at once; otherwise the two half-warps look at two consecutive slots per pass.
+        const int u_lo = s_lo >> 2;
+        const int u_first = u_lo + (((u_lo & 1) != hsel) ? 1 : 0);
+        uint2 av_next = make_uint2(0u, 0u);
+        if (4 * u_first < t) av_next = *reinterpret_cast<const uint2*>(Arow + 4 * u_first);
+        for (int u = u_first; u <= (t >> 2); u += 2) {
+#if SMCT_X_AVNEXT
+          const uint2 av = av_next;
+          av_next = make_uint2(0u, 0u);
+          if (4 * (u + 2) < t) av_next = *reinterpret_cast<const uint2*>(Arow + 4 * (u + 2));   // requested one unit ahead
+#else
+          uint2 av = make_uint2(0u, 0u);
+          if (4 * u < t) av = *reinterpret_cast<const uint2*>(Arow + 4 * u);
+#endif
+          if (4 * u >= s_lo && 4 * u + 3 < t) {
+            const uint32_t x0 = __shfl_sync(SMCT_FULL_MASK, av.x, 0), y0 = __shfl_sync(SMCT_FULL_MASK, av.y, 0);
+            if (__all_sync(SMCT_FULL_MASK, av.x == x0 && av.y == y0)) {
+              if (ncols + 4 > 16) {
+                attn::process_group(st, cd, ncols, Qf, Ksb, Vsb, P, inv_qk, lane);
+                ncols = 0;
+              }
+              if (lane < 4) {
+                const uint32_t w = lane < 2 ? x0 : y0;
+                const uint32_t row = (lane & 1) ? (w >> 16) : (w & 0xFFFFu);
+                cd[ncols + lane] = make_uint2(((uint32_t)(4 * u + lane) << 16) | row, 16u << 8);
+                attn::prefetch_column(Ksb, Vsb, 4 * u + lane, (int)row, P);
+              }
+              __syncwarp();
+              ncols += 4;
+              continue;
+            }
+          }
 #pragma unroll 1
-          for (int pass = 0; pass < 4; ++pass) {
-            const int s = 8 * blk + 2 * pass + hsl;
-            const uint32_t w = pass < 2 ? (pass == 0 ? av.x : av.y) : (pass == 2 ? av.z : av.w);
+          for (int pass = 0; pass < 2; ++pass) {
+            const int s = 4 * u + 2 * pass + hsl;
+            const uint32_t w = pass == 0 ? av.x : av.y;
             int aval = hsl ? (int)(w >> 16) : (int)(w & 0xFFFFu);
             if (s == t) aval = myq;                       // the current slot: the particle's own row
             const int prev = __shfl_up_sync(SMCT_FULL_MASK, aval, 1);
@@ -301,6 +336,7 @@ __global__ void __launch_bounds__(FNT, 1) fused_tc_forward_kernel(const FusedArg
                 const uint32_t above = (hsl ? (hb >> 16) : (hb & 0xFFFFu)) >> (l15 + 1);
                 const int hi = above ? (l15 + __ffs((int)above)) : 16;
                 cd[col] = make_uint2(((uint32_t)s << 16) | (uint32_t)aval, ((uint32_t)hi << 8) | (uint32_t)l15);
+                attn::prefetch_column(Ksb, Vsb, s, aval, P);
               }
               __syncwarp();
               ncols += __popc(take);
