@@ -51,12 +51,14 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=None, help="sequences in the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--sigma2", type=float, default=0.5, help="variance of the k,q,v,z noises (run.py default 0.5)")
+    ap.add_argument("--sigma-obs", type=float, default=0.5, help="observation variance of the Gaussian weights")
     return ap.parse_args()
 
 
-def workload_desc(name, B, P, S, D, dff, F):
+def workload_desc(name, B, P, S, D, dff, F, sigma2=0.5, sigma_obs=0.5):
     return ("%s: bs=%d particles=%d d_model=%d dff=%d seq_len=%d F=%d, 1 layer, 1 head, full_model, "
-            "gaussian weights, sigma2=0.5, sigma_obs=0.5" % (name.upper(), B, P, D, dff, S, F))
+            "gaussian weights, sigma2=%g, sigma_obs=%g" % (name.upper(), B, P, D, dff, S, F, sigma2, sigma_obs))
 
 
 # --------------------------------------------------------------------------------------------------
@@ -116,7 +118,7 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------------
 # CPU arm: reference-equivalent eager restatement (oracle/ref_eager_torch.py) on the host cores
 # --------------------------------------------------------------------------------------------------
-def cpu_reference_run(wl, sample_B, steps, warmup):
+def cpu_reference_run(wl, sample_B, steps, warmup, sigma2=0.5, sigma_obs=0.5):
     """Times the reference-equivalent CPU path.  The only place bench.py executes oracle/ code."""
     import torch
     from oracle import ref_eager_torch as E
@@ -126,8 +128,8 @@ def cpu_reference_run(wl, sample_B, steps, warmup):
     _, P, S, D, dff, F, alpha, var = WORKLOADS[wl]
     cores = len(os.sched_getaffinity(0))
     torch.set_num_threads(cores)
-    cfg = O.Config(B=sample_B, P=P, S=S, D=D, dff=dff, F_x=F, F_y=F)
-    p = utils.init_parameters(D, dff, F, F, sigma2=0.5)
+    cfg = O.Config(B=sample_B, P=P, S=S, D=D, dff=dff, F_x=F, F_y=F, sigma_obs=sigma_obs)
+    p = utils.init_parameters(D, dff, F, F, sigma2=sigma2)
     tp = {k: torch.from_numpy(v.reshape(()) if k.startswith("logvar") else v) for k, v in p.items()}
     x, y = utils.synthetic_ar1(sample_B, S, F, alpha, var)
     tx, ty = torch.from_numpy(x), torch.from_numpy(y)
@@ -159,12 +161,12 @@ def run_reference(args):
     wl = args.workload
     B, P, S, D, dff, F, _, _ = WORKLOADS[wl]
     sample = args.cpu_sample or default_cpu_sample(wl)
-    r = cpu_reference_run(wl, sample, args.steps, args.warmup)
+    r = cpu_reference_run(wl, sample, args.steps, args.warmup, args.sigma2, args.sigma_obs)
     line = {
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["s_per_step"] * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_desc(wl, B, P, S, D, dff, F), "sample_sequences_per_step": sample,
+        "config": {"workload": workload_desc(wl, B, P, S, D, dff, F, args.sigma2, args.sigma_obs), "sample_sequences_per_step": sample,
                    "device": "host CPU, %d threads" % r["cores"]},
         "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -219,7 +221,7 @@ def run_b200(args):
     B, P, S, D, dff, F, alpha, var = WORKLOADS[wl]
     if args.batch:
         B = args.batch
-    p_host = utils.init_parameters(D, dff, F, F, sigma2=0.5)
+    p_host = utils.init_parameters(D, dff, F, F, sigma2=args.sigma2)
     params = {k: torch.as_tensor(v, device=dev) for k, v in p_host.items()}
     # every rank works on its own sequences: global sequence index = rank*B + b (RNG keyed by it)
     x_host, y_host = utils.synthetic_ar1(B, S, F, alpha, var, seed=1234 + rank)
@@ -257,7 +259,8 @@ def run_b200(args):
         for c in range(n_chunks):
             b0, b1 = c * chunk, min(B, (c + 1) * chunk)
             n = b1 - b0
-            shape = F_.make_shape(n, P, S, D, dff=dff, F_x=F, F_y=F, algo=args.algo, b_global0=rank * B + b0)
+            shape = F_.make_shape(n, P, S, D, dff=dff, F_x=F, F_y=F, algo=args.algo, b_global0=rank * B + b0,
+                                  sigma_obs=args.sigma_obs)
             out = dict(pred=pred[b0:b1], pred_resampl=pred_r[b0:b1], w=w[b0:b1], K=Kc[:n], V=Vc[:n], R=Rc[:n],
                        loss_sums=loss_sums[c])
             F_.forward(shape, params, xd[b0:b1], yd[b0:b1], seed=seed, want=("loss_sums",), out=out)
@@ -266,7 +269,7 @@ def run_b200(args):
 
     def loss_from_sums(ls):
         # regression-era loss (pyc): mean 0.5*sum_n ||n||^2/sigma_n^2 + mean 0.5*||y-pred_resampl||^2/Sigma_obs
-        return _loss_from_sums(ls.sum(0).tolist(), float(B) * P * S, sigma_obs=0.5, variant="pyc")[0]
+        return _loss_from_sums(ls.sum(0).tolist(), float(B) * P * S, sigma_obs=args.sigma_obs, variant="pyc")[0]
 
     def barrier():
         if dist is not None:
@@ -333,7 +336,7 @@ def run_b200(args):
     # ---------------- CPU baseline (rank 0, N=1 only) ----------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        r = cpu_reference_run(wl, args.cpu_sample or default_cpu_sample(wl), 1, 0)
+        r = cpu_reference_run(wl, args.cpu_sample or default_cpu_sample(wl), 1, 0, args.sigma2, args.sigma_obs)
         cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
     if rank == 0:
@@ -347,7 +350,7 @@ def run_b200(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_desc(wl, B, P, S, D, dff, F), "per_gpu_batch": B, "chunk_sequences": chunk,
+            "config": {"workload": workload_desc(wl, B, P, S, D, dff, F, args.sigma2, args.sigma_obs), "per_gpu_batch": B, "chunk_sequences": chunk,
                        "chunks_per_step": n_chunks, "algo": algo_used, "rng": "device Philox4x32-10 + Box-Muller",
                        "l2": "working set per chunk (%.1f GB state) >> 126 MB L2; no flush needed" % (chunk * state_per_seq / 1e9),
                        "parallelism": "batch-sharded replicas, no collective in the forward"},
