@@ -52,11 +52,15 @@ struct FusedArgs {
   double* loss_sums;
 };
 
-struct FusedCommon {           // per-sequence bookkeeping shared by both fused kernels
+struct FusedResampleScratch {  // used only between the tiles of two timesteps (draw + genealogy update)
   double cdf[FPMAX];
-  float lw[FPMAX];
   unsigned int keys[FPMAX];
-  unsigned short Lq[FPMAX], pos[FPMAX], src[FPMAX], anc[FPMAX];
+  unsigned short src[FPMAX], anc[FPMAX];
+};
+
+struct FusedCommon {           // per-sequence bookkeeping shared by both fused kernels
+  float lw[FPMAX];
+  unsigned short Lq[FPMAX], pos[FPMAX];
   float rowbuf[4][FD];       // xln, q_, k_, v_ of the current step
   float stdtab[4][FD];       // exp(0.5 logvar) for k,q,v,z
   float ivar[4][FD];         // exp(-logvar)
@@ -66,6 +70,7 @@ struct FusedCommon {           // per-sequence bookkeeping shared by both fused 
 
 struct FusedSmem {
   FusedCommon c;
+  FusedResampleScratch rs;
   float Zs[FTILE * FLD];
   float Os[FTILE * FLD];
   float Hs[FTILE * FLD];
@@ -122,7 +127,7 @@ __device__ __forceinline__ void wblock_commit(float* WBbuf, int tid, const float
 // logsumexp normalise, TF-CPU categorical draw (fp64 sequential CDF in logical particle order), then the
 // genealogy update: sort the new particles by the position of their ancestor (tree order) and rewrite the
 // ancestry rows.  Called by all threads of the CTA once per timestep.
-__device__ __forceinline__ void fused_resample_update(FusedCommon& c, const FusedArgs& a, int b, int t,
+__device__ __forceinline__ void fused_resample_update(FusedCommon& c, FusedResampleScratch& rx, const FusedArgs& a, int b, int t,
                                                       unsigned short*& Acur, unsigned short*& Anxt, int& cur_is_A0) {
   const int tid = threadIdx.x;
   const int P = a.P, S = a.S, Sa = a.Sa;
@@ -143,12 +148,12 @@ __device__ __forceinline__ void fused_resample_update(FusedCommon& c, const Fuse
     const float lg = raw - lse;
     if (a.w) a.w[(bP + p) * S + t] = expf(lg);
     if (a.logw) a.logw[((long long)t * a.B + b) * P + p] = raw;
-    c.cdf[p] = isfinite(lg) ? exp((double)lg - (double)m2) : 0.0;
+    rx.cdf[p] = isfinite(lg) ? exp((double)lg - (double)m2) : 0.0;
   }
   __syncthreads();
   if (tid == 0) {
     double run = 0.0;
-    for (int p = 0; p < P; ++p) { run += c.cdf[p]; c.cdf[p] = run; }
+    for (int p = 0; p < P; ++p) { run += rx.cdf[p]; rx.cdf[p] = run; }
     c.dred[0] = run;
   }
   __syncthreads();
@@ -166,12 +171,12 @@ __device__ __forceinline__ void fused_resample_update(FusedCommon& c, const Fuse
       int lo = 0, hi = P;
       while (lo < hi) {
         const int mid = (lo + hi) >> 1;
-        if (c.cdf[mid] <= target) lo = mid + 1; else hi = mid;
+        if (rx.cdf[mid] <= target) lo = mid + 1; else hi = mid;
       }
       idx = min(lo, P - 1);
     }
     if (a.i_out) a.i_out[ti] = idx;
-    c.anc[p] = (unsigned short)idx;
+    rx.anc[p] = (unsigned short)idx;
   }
   __syncthreads();
 
@@ -182,24 +187,24 @@ __device__ __forceinline__ void fused_resample_update(FusedCommon& c, const Fuse
     int np2 = 1;
     while (np2 < P) np2 <<= 1;
     for (int p = tid; p < np2; p += FNT)
-      c.keys[p] = (p < P) ? (((unsigned int)c.pos[c.anc[p]] << 16) | (unsigned int)p) : 0xFFFFFFFFu;
+      rx.keys[p] = (p < P) ? (((unsigned int)c.pos[rx.anc[p]] << 16) | (unsigned int)p) : 0xFFFFFFFFu;
     __syncthreads();
     for (int k = 2; k <= np2; k <<= 1) {
       for (int j = k >> 1; j > 0; j >>= 1) {
         for (int i = tid; i < np2; i += FNT) {
           const int ixj = i ^ j;
           if (ixj > i) {
-            const unsigned int x = c.keys[i], yv = c.keys[ixj];
+            const unsigned int kx = rx.keys[i], yv = rx.keys[ixj];
             const bool up = ((i & k) == 0);
-            if ((x > yv) == up) { c.keys[i] = yv; c.keys[ixj] = x; }
+            if ((kx > yv) == up) { rx.keys[i] = yv; rx.keys[ixj] = kx; }
           }
         }
         __syncthreads();
       }
     }
     for (int qn = tid; qn < P; qn += FNT) {
-      const unsigned int key = c.keys[qn];
-      c.src[qn] = (unsigned short)(key >> 16);
+      const unsigned int key = rx.keys[qn];
+      rx.src[qn] = (unsigned short)(key >> 16);
       c.Lq[qn] = (unsigned short)(key & 0xFFFFu);
     }
     __syncthreads();
@@ -208,7 +213,7 @@ __device__ __forceinline__ void fused_resample_update(FusedCommon& c, const Fuse
     const int nch = (t >> 3) + 1;
     for (int i = tid; i < P * nch; i += FNT) {
       const int qn = i / nch, ch = i - qn * nch;
-      const int sq = c.src[qn];
+      const int sq = rx.src[qn];
       uint4 v = *reinterpret_cast<const uint4*>(Acur + (long long)sq * Sa + 8 * ch);
       if ((t >> 3) == ch) {  // patch slot t (little-endian: element e is half (e&1) of word (e>>1))
         const int e = t & 7;
@@ -509,7 +514,7 @@ __global__ void __launch_bounds__(FNT, 1) fused_forward_kernel(const FusedArgs a
       }
     }
 
-    fused_resample_update(sm.c, a, b, t, Acur, Anxt, cur_is_A0);
+    fused_resample_update(sm.c, sm.rs, a, b, t, Acur, Anxt, cur_is_A0);
   }  // timesteps
 
   for (int p = tid; p < P; p += FNT) a.pos_out[bP + p] = sm.c.pos[p];

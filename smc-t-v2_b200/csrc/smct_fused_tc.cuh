@@ -26,12 +26,15 @@ struct FusedTcSmem {
   float Os[FTILE * FLD];                              // fp32 tile: z_ -> LN1 input -> o -> LN2 input -> r
   __align__(128) unsigned char ZH[2 * tc::A_PART_BYTES];   // A operand: z_ (h,m), later the FFN hidden chunk
   __align__(128) unsigned char Ob[2 * tc::A_PART_BYTES];   // A operand: o = LN1(z + x) (h,m)
-  __align__(128) unsigned char Wzb[2 * tc::B_PART_BYTES];  // B operand: Wz (h,m)
-  __align__(128) unsigned char Wc[2][4 * tc::B_PART_BYTES];// B operands: W1 chunk (h,m) + W2 chunk (h,m), double-buffered
+  __align__(128) unsigned char W1all[FF / FD][2 * tc::B_PART_BYTES];   // B operands: the four W1 chunks (h,m), resident for the whole kernel
+  // stream buffers: Ws[0] <- Wz, W2 chunk 1, W2 chunk 3 ; Ws[1] <- W2 chunk 0, W2 chunk 2 (per tile).  Between the tiles
+  // of two timesteps the same bytes hold the scratch of the draw / genealogy update (FusedResampleScratch, 16 KB).
+  __align__(128) unsigned char Ws[2][2 * tc::B_PART_BYTES];
   __align__(8) uint2 cdesc[FNT / 32][16];             // per-warp column descriptors of the attention groups
-  __align__(8) uint64_t mbar;
+  __align__(8) uint64_t mbar_z, mbar_h[FF / FD], mbar_r;
   uint32_t tmem_slot;
 };
+static_assert(sizeof(FusedResampleScratch) <= 2 * 2 * tc::B_PART_BYTES, "resample scratch must fit the weight stream buffers");
 static_assert(sizeof(FusedTcSmem) <= 227 * 1024, "fused tc kernel shared memory exceeds 227 KB");
 
 __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
@@ -39,6 +42,7 @@ __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 __device__ __forceinline__ void copy_block_async(unsigned char* dst, const unsigned char* src, int bytes) {
   for (int i = threadIdx.x; i < bytes / 16; i += FNT) cp_async16(dst + 16 * i, src + 16 * i);
 }
@@ -119,7 +123,7 @@ __global__ void __launch_bounds__(FNT, 1) fused_tc_forward_kernel(const FusedArg
   const uint32_t tlane = ((uint32_t)((wid & 3) * 32)) << 16;
   const uint32_t idesc = tc::make_idesc(128, 64);
   double dloss_q = 0.0, dloss_z = 0.0;            // thread 0 only
-  uint32_t mphase = 0;
+  uint32_t ph_z = 0, ph_h = 0, ph_r = 0;   // phase parities of the MMA completion barriers
 
   for (int i = tid; i < P; i += FNT) { sm.c.Lq[i] = (unsigned short)i; sm.c.pos[i] = (unsigned short)i; }
   if (tid < 4 * FD) {
@@ -136,13 +140,23 @@ __global__ void __launch_bounds__(FNT, 1) fused_tc_forward_kernel(const FusedArg
   for (int i = tid; i < FF; i += FNT) sm.b1[i] = a.p.b1[i];
   for (int i = tid; i < FD * Fy; i += FNT) sm.Wo[i] = a.p.Wo[i];
   if (tid == 0) sm.hdr = *reinterpret_cast<const TcHeader*>(a.wtc + (size_t)(1 + 2 * (FF / FD)) * 2 * tc::B_PART_BYTES);
-  if (wid == 0) tc::tmem_alloc(&sm.tmem_slot, 256);
-  if (tid == 0) { tc::mbar_init(&sm.mbar, 1); tc::fence_mbar_init(); }
+  if (wid == 0) tc::tmem_alloc(&sm.tmem_slot, 512);
+  if (tid == 0) {
+    tc::mbar_init(&sm.mbar_z, 1); tc::mbar_init(&sm.mbar_r, 1);
+    for (int c = 0; c < FF / FD; ++c) tc::mbar_init(&sm.mbar_h[c], 1);
+    tc::fence_mbar_init();
+  }
+  for (int c = 0; c < FF / FD; ++c)   // W1 stays in shared memory for all tiles and timesteps
+    copy_block_async(sm.W1all[c], a.wtc + (size_t)(1 + 2 * c) * 2 * tc::B_PART_BYTES, 2 * tc::B_PART_BYTES);
+  cp_async_commit();
+  cp_async_wait_all();
+  tc::fence_async_smem();
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem = sm.tmem_slot;
-  const uint32_t tD_z = tmem, tD_h = tmem + 64, tD_r = tmem + 128;
+  const uint32_t tD_z = tmem, tD_h = tmem + 64, tD_r = tmem + 64 + FF;   // z | four hidden chunks | r
+  FusedResampleScratch& rsx = *reinterpret_cast<FusedResampleScratch*>(&sm.Ws[0][0]);
 
   for (int t = 0; t < S; ++t) {
     const int s_lo = (a.attn_window >= 0 && t > a.attn_window) ? t - a.attn_window : 0;
@@ -158,8 +172,8 @@ __global__ void __launch_bounds__(FNT, 1) fused_tc_forward_kernel(const FusedArg
       const int q0 = g * FTILE;
       const int np = min(FTILE, P - q0);
       // weight blocks for this tile: Wz and FFN chunk 0 travel while the tile does attention
-      copy_block_async(sm.Wzb, a.wtc, 2 * tc::B_PART_BYTES);
-      copy_block_async(sm.Wc[0], a.wtc + 2 * tc::B_PART_BYTES, 4 * tc::B_PART_BYTES);
+      copy_block_async(sm.Ws[0], a.wtc, 2 * tc::B_PART_BYTES);                                      // Wz
+      copy_block_async(sm.Ws[1], a.wtc + (size_t)2 * 2 * tc::B_PART_BYTES, 2 * tc::B_PART_BYTES);   // W2 chunk 0
       cp_async_commit();
 
       // =========================== phase A1: noise, slot-t rows (fp32 + fp16 split), q tile ===========================
@@ -403,39 +417,48 @@ __global__ void __launch_bounds__(FNT, 1) fused_tc_forward_kernel(const FusedArg
 
       // =========================== phase B: dense tile on the tensor cores ===========================
       if (tid == 0) {
-        tc::mma_block_bf16x3(tD_z, tc::smem_u32(sm.ZH), tc::smem_u32(sm.Wzb), tc::B_PART_BYTES, idesc, false);
-        tc::commit(&sm.mbar);
+        tc::mma_block_bf16x3(tD_z, tc::smem_u32(sm.ZH), tc::smem_u32(sm.Ws[0]), tc::B_PART_BYTES, idesc, false);
+        tc::commit(&sm.mbar_z);
       }
-      tc::mbar_wait(&sm.mbar, mphase);
-      mphase ^= 1;
-      tc::fence_after_sync();
       const bool eact = er < np;
       const int eL = sm.c.Lq[eact ? (q0 + er) : (P - 1)];
       const int n0 = 16 * ecq;
       float val[16];
+      float ezv[16];   // z noise of this thread's 16 columns: generated while the tensor core works
+      {
+        const unsigned long long gbp = (unsigned long long)(a.b_global0 + b) * (unsigned long long)P + eL;
+#pragma unroll
+        for (int gq = 0; gq < 4; ++gq) {
+          const int n = n0 + 4 * gq;
+          if (a.eps) {
+            const float4 t3 = *reinterpret_cast<const float4*>(a.eps + (3LL * S) * ((long long)a.B * P * FD) +
+                                                               ((long long)t * a.B + b) * P * FD + (long long)eL * FD + n);
+            ezv[4 * gq] = t3.x; ezv[4 * gq + 1] = t3.y; ezv[4 * gq + 2] = t3.z; ezv[4 * gq + 3] = t3.w;
+          } else {
+            philox_normal4(a.seed, 3u, (uint32_t)t, gbp * 16ull + (n >> 2), &ezv[4 * gq]);
+          }
+        }
+      }
+      tc::mbar_wait(&sm.mbar_z, ph_z);
+      ph_z ^= 1;
+      tc::fence_after_sync();
+      // Wz has been consumed: W2 chunk 1 travels into its buffer during the LN1 epilogue
+      copy_block_async(sm.Ws[0], a.wtc + (size_t)4 * 2 * tc::B_PART_BYTES, 2 * tc::B_PART_BYTES);
+      cp_async_commit();
       {  // ---- z = dense(z_) + noise ; LN1(z + x) ----
         tmem_ld16(tD_z + tlane + n0, val);
         const float zscale = sm.rs[er] * sm.hdr.inv_wz;
-        const unsigned long long gbp = (unsigned long long)(a.b_global0 + b) * (unsigned long long)P + eL;
         float s1 = 0.f;
 #pragma unroll
         for (int gq = 0; gq < 4; ++gq) {
           const int n = n0 + 4 * gq;
-          float ez[4];
-          if (a.eps) {
-            const float4 t3 = *reinterpret_cast<const float4*>(a.eps + (3LL * S) * ((long long)a.B * P * FD) +
-                                                               ((long long)t * a.B + b) * P * FD + (long long)eL * FD + n);
-            ez[0] = t3.x; ez[1] = t3.y; ez[2] = t3.z; ez[3] = t3.w;
-          } else {
-            philox_normal4(a.seed, 3u, (uint32_t)t, gbp * 16ull + (n >> 2), ez);
-          }
           const float4 zold = *reinterpret_cast<const float4*>(&sm.Os[er * FLD + n]);
           const float z_[4] = {zold.x, zold.y, zold.z, zold.w};
           float nzv[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const float zp = fmaf(val[4 * gq + e], zscale, sm.bz[n + e]);   // scale is a power of two: exact
-            const float z = __fadd_rn(zp, __fmul_rn(sm.c.stdtab[3][n + e], ez[e]));
+            const float z = __fadd_rn(zp, __fmul_rn(sm.c.stdtab[3][n + e], ezv[4 * gq + e]));
             nzv[e] = (a.noise_z_mode == SMCT_NOISE_Z_CHECKOUT) ? (z - z_[e]) : (z - zp);
             loss_z = eact ? fmaf(nzv[e] * nzv[e], sm.c.ivar[3][n + e], loss_z) : loss_z;
             val[4 * gq + e] = z + sm.c.rowbuf[0][n + e];
@@ -472,43 +495,46 @@ __global__ void __launch_bounds__(FNT, 1) fused_tc_forward_kernel(const FusedArg
       tc::fence_before_sync();
       __syncthreads();
       tc::fence_after_sync();
-      // ---- FFN: 4 chunks of 64 hidden units ----
+      // ---- FFN: the four first GEMMs (o · W1 chunk, W1 resident) are issued at once into four TMEM ranges; the relu /
+      //      split epilogue of chunk c then overlaps the tensor-core work of the later chunks and of the second GEMMs ----
+      if (tid == 0) {
+        for (int c = 0; c < FF / FD; ++c) {
+          tc::mma_block_bf16x3(tD_h + FD * c, tc::smem_u32(sm.Ob), tc::smem_u32(sm.W1all[c]), tc::B_PART_BYTES, idesc, false);
+          tc::commit(&sm.mbar_h[c]);
+        }
+      }
       for (int c = 0; c < FF / FD; ++c) {
-        unsigned char* wb = sm.Wc[c & 1];
-        if (tid == 0) {
-          tc::mma_block_bf16x3(tD_h, tc::smem_u32(sm.Ob), tc::smem_u32(wb), tc::B_PART_BYTES, idesc, false);
-          tc::commit(&sm.mbar);
-        }
-        tc::mbar_wait(&sm.mbar, mphase);   // also covers the previous chunk's second GEMM: ZH and Wc[(c+1)&1] are free
-        mphase ^= 1;
+        tc::mbar_wait(&sm.mbar_h[c], ph_h);
         tc::fence_after_sync();
-        if (c + 1 < FF / FD) {
-          copy_block_async(sm.Wc[(c + 1) & 1], a.wtc + 2 * tc::B_PART_BYTES + (size_t)(c + 1) * 4 * tc::B_PART_BYTES,
-                           4 * tc::B_PART_BYTES);
-          cp_async_commit();
-        }
-        tmem_ld16(tD_h + tlane + n0, val);
+        tmem_ld16(tD_h + FD * c + tlane + n0, val);
         const float hscale = sm.hdr.inv_o * sm.hdr.inv_w1;
+        float hv[16];
 #pragma unroll
-        for (int gq = 0; gq < 4; ++gq) {
-          const int n = n0 + 4 * gq;
-          float h[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) h[e] = fmaxf(fmaf(val[4 * gq + e], hscale, sm.b1[c * FD + n + e]), 0.f) * sm.hdr.s_h;
-          tc::store_a4(sm.ZH, er, n, h);
+        for (int j = 0; j < 16; ++j) hv[j] = fmaxf(fmaf(val[j], hscale, sm.b1[c * FD + n0 + j]), 0.f) * sm.hdr.s_h;
+        if (c > 0) {   // the previous second GEMM has read ZH and its W2 buffer: both may be refilled
+          tc::mbar_wait(&sm.mbar_r, ph_r);
+          ph_r ^= 1;
+          tc::fence_after_sync();
+          if (c + 1 < FF / FD) {
+            copy_block_async(sm.Ws[(c + 1 + 1) & 1], a.wtc + (size_t)(2 + 2 * (c + 1)) * 2 * tc::B_PART_BYTES, 2 * tc::B_PART_BYTES);
+            cp_async_commit();
+          }
         }
-        cp_async_wait_all();
+#pragma unroll
+        for (int gq = 0; gq < 4; ++gq) tc::store_a4(sm.ZH, er, n0 + 4 * gq, &hv[4 * gq]);
+        if (c == 0 || c + 1 == FF / FD) cp_async_wait_all(); else cp_async_wait_1();   // W2 chunk c has landed (chunk c+1 may still travel)
         tc::fence_async_smem();
         tc::fence_before_sync();
         __syncthreads();
         tc::fence_after_sync();
         if (tid == 0) {
-          tc::mma_block_bf16x3(tD_r, tc::smem_u32(sm.ZH), tc::smem_u32(wb + 2 * tc::B_PART_BYTES), tc::B_PART_BYTES, idesc, c > 0);
-          if (c + 1 == FF / FD) tc::commit(&sm.mbar);
+          tc::mma_block_bf16x3(tD_r, tc::smem_u32(sm.ZH), tc::smem_u32(sm.Ws[(c + 1) & 1]), tc::B_PART_BYTES, idesc, c > 0);
+          tc::commit(&sm.mbar_r);
         }
       }
-      tc::mbar_wait(&sm.mbar, mphase);
-      mphase ^= 1;
+      ph_h ^= 1;
+      tc::mbar_wait(&sm.mbar_r, ph_r);
+      ph_r ^= 1;
       tc::fence_after_sync();
       {  // ---- r = LN2(ffn + b2 + o) ; R row store ----
         tmem_ld16(tD_r + tlane + n0, val);
@@ -585,7 +611,7 @@ __global__ void __launch_bounds__(FNT, 1) fused_tc_forward_kernel(const FusedArg
         for (int i = 0; i < 16; ++i) { dloss_q += (double)sm.c.red[i]; dloss_z += (double)sm.c.red[16 + i]; }
       }
     }
-    fused_resample_update(sm.c, a, b, t, Acur, Anxt, cur_is_A0);
+    fused_resample_update(sm.c, rsx, a, b, t, Acur, Anxt, cur_is_A0);
   }  // timesteps
 
   for (int p = tid; p < P; p += FNT) a.pos_out[bP + p] = sm.c.pos[p];
@@ -595,7 +621,7 @@ __global__ void __launch_bounds__(FNT, 1) fused_tc_forward_kernel(const FusedArg
   }
   tc::fence_before_sync();
   __syncthreads();
-  if (wid == 0) tc::tmem_dealloc(tmem, 256);
+  if (wid == 0) tc::tmem_dealloc(tmem, 512);
 }
 
 }  // namespace smct
