@@ -60,6 +60,7 @@ struct BwdArgs {
   const unsigned short *node_p, *node_L;  // (N) representative final particle, logical ancestor id
   const float* node_m;                    // (N) multiplicity
   float *Zm, *dZm, *stat;                 // (N,D), (N,D), (N,2) per node
+  float* Qm;                              // (N,D) q row of the node (k_, noise regenerated once by bwd_attn_fwd)
   float *dq_sum, *dk_sum, *dv_sum, *dxln_sum, *dkx_sum, *dvx_sum;   // (B,S,D)
   float* rep;                             // nrep x layout.total gradient replicas
   int nrep;
@@ -220,7 +221,7 @@ __global__ void __launch_bounds__(256) bwd_attn_fwd_kernel(const BwdArgs a) {
 #pragma unroll
     for (int k = 0; k < KD; ++k) {
       const int d = lane + 32 * k;
-      if (d < D) a.Zm[u * D + d] = acc[k] / l;
+      if (d < D) { a.Zm[u * D + d] = acc[k] / l; a.Qm[u * D + d] = q[k]; }
     }
     if (lane == 0) { a.stat[u * 2] = m; a.stat[u * 2 + 1] = l; }
   }
@@ -439,94 +440,115 @@ __global__ void __launch_bounds__(NT) bwd_dense_kernel(const BwdArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------
-// attention backward: BWD_G CTAs per sequence share its nodes (strided, so that long and short rows mix);
-// warp per node; dk/dv summed over the CTA's nodes in shared memory, then added to the (B,S,D) row sums
+// attention backward: BWD_G CTAs per sequence share its nodes (strided, so that long and short rows mix).
+// Every warp of a CTA owns the target slots t = w, w+16, w+32, ... (TJ of them per pass of 16*TJ slots) and walks over
+// ALL nodes of the CTA: the dk/dv sums of its slots stay in registers (no shared-memory atomics — those are CAS loops
+// for fp32), dq of a node is reduced over the warps with one native global RED per element.
 // ------------------------------------------------------------------------------------------
 constexpr int BWD_G = 8;        // CTAs per sequence
 constexpr int BWD_ANT = 512;    // threads per CTA
+constexpr int BWD_TJ = 8;       // target slots per warp and pass
 
 template <int KD>
 __global__ void __launch_bounds__(BWD_ANT) bwd_attn_bwd_kernel(const BwdArgs a) {
-  extern __shared__ float sm[];
   const int D = a.D, S = a.S;
-  float* dKs = sm;                 // S*D: sum over the CTA's nodes of dL/dk_tau (attention + direct noise term)
-  float* dVs = dKs + S * D;
-  float* dKX = dVs + S * D;        // direct terms only, with the sign of d/d kx
-  float* dVX = dKX + S * D;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   constexpr int NWA = BWD_ANT / 32;
   const int b = blockIdx.x / BWD_G, g = blockIdx.x % BWD_G;
-  const float std_q = expf(0.5f * a.p.logvar_q[0]);
   const float sqrt_d = sqrtf((float)D);
   const float c_k = expf(-a.p.logvar_k[0]) * a.inv_n, c_v = expf(-a.p.logvar_v[0]) * a.inv_n;
-  for (int i = tid; i < 4 * S * D; i += BWD_ANT) sm[i] = 0.f;
-  __syncthreads();
   const long long u_begin = a.node_off[(long long)b * S], u_end = a.node_off[(long long)(b + 1) * S];
-  for (long long u = u_begin + g + (long long)wid * BWD_G; u < u_end; u += (long long)BWD_G * NWA) {
-    const int bs = a.node_bs[u];
-    const int s = bs % S;
-    const long long bp = (long long)b * a.P + a.node_p[u];
-    const int L = a.node_L[u];
-    const float mult = a.node_m[u];
-    const float* Kp = a.K + bp * S * D;
-    const float* Vp = a.V + bp * S * D;
-    const int s_lo = (a.attn_window >= 0 && s > a.attn_window) ? s - a.attn_window : 0;
-    float q[KD], dz[KD], dq[KD], part0 = 0.f;
+  for (int tbase = 0; tbase < S; tbase += NWA * BWD_TJ) {
+    float dk[BWD_TJ][KD], dv[BWD_TJ][KD];
 #pragma unroll
-    for (int k = 0; k < KD; ++k) {
-      const int d = lane + 32 * k;
-      const bool ok = d < D;
-      q[k] = ok ? __fadd_rn(a.q_[(long long)bs * D + d], __fmul_rn(std_q, bwd_eps(a, 1, b, s, L, d))) : 0.f;
-      dz[k] = ok ? a.dZm[u * D + d] : 0.f;
-      const float zz = ok ? a.Zm[u * D + d] : 0.f;
-      part0 = fmaf(dz[k], zz, part0);
-      dq[k] = 0.f;
-    }
-    const float delta = warp_sum(part0);     // sum_tau a_tau (dz . v_tau) = dz . z_
-    const float m = a.stat[u * 2], l = a.stat[u * 2 + 1];
-    for (int t = s_lo; t <= s; ++t) {
-      float pk = 0.f, pv = 0.f, kr[KD], vr[KD];
+    for (int j = 0; j < BWD_TJ; ++j)
+#pragma unroll
+      for (int k = 0; k < KD; ++k) { dk[j][k] = 0.f; dv[j][k] = 0.f; }
+    for (long long u = u_begin + g; u < u_end; u += BWD_G) {
+      const int bs = a.node_bs[u];
+      const int s = bs % S;
+      if (s < tbase + wid) continue;                       // no target slot of this warp is visible to the node
+      const int s_lo = (a.attn_window >= 0 && s > a.attn_window) ? s - a.attn_window : 0;
+      const long long bp = (long long)b * a.P + a.node_p[u];
+      const float* Kp = a.K + bp * S * D;
+      const float* Vp = a.V + bp * S * D;
+      float q[KD], dz[KD], dq[KD], part0 = 0.f;
 #pragma unroll
       for (int k = 0; k < KD; ++k) {
         const int d = lane + 32 * k;
-        kr[k] = (d < D) ? Kp[(long long)t * D + d] : 0.f;
-        vr[k] = (d < D) ? Vp[(long long)t * D + d] : 0.f;
-        pk = fmaf(q[k], kr[k], pk);
-        pv = fmaf(dz[k], vr[k], pv);
+        const bool ok = d < D;
+        q[k] = ok ? a.Qm[u * D + d] : 0.f;
+        dz[k] = ok ? a.dZm[u * D + d] : 0.f;
+        const float zz = ok ? a.Zm[u * D + d] : 0.f;
+        part0 = fmaf(dz[k], zz, part0);
+        dq[k] = 0.f;
       }
-      const float sc = warp_sum(pk) / sqrt_d;
-      const float dA = warp_sum(pv);
-      const float at = expf(sc - m) / l;
-      const float dS = at * (dA - delta) / sqrt_d;
+      const float delta = warp_sum(part0);     // sum_tau a_tau (dz . v_tau) = dz . z_
+      const float m = a.stat[u * 2], l = a.stat[u * 2 + 1];
+      bool any = false;
 #pragma unroll
-      for (int k = 0; k < KD; ++k) {
-        const int d = lane + 32 * k;
-        if (d < D) {
+      for (int j = 0; j < BWD_TJ; ++j) {
+        const int t = tbase + wid + NWA * j;
+        if (t > s || t < s_lo) continue;                   // warp-uniform
+        any = true;
+        float pk = 0.f, pv = 0.f, kr[KD], vr[KD];
+#pragma unroll
+        for (int k = 0; k < KD; ++k) {
+          const int d = lane + 32 * k;
+          kr[k] = (d < D) ? Kp[(long long)t * D + d] : 0.f;
+          vr[k] = (d < D) ? Vp[(long long)t * D + d] : 0.f;
+          pk = fmaf(q[k], kr[k], pk);
+          pv = fmaf(dz[k], vr[k], pv);
+        }
+        const float sc = warp_sum(pk) / sqrt_d;
+        const float dA = warp_sum(pv);
+        const float at = expf(sc - m) / l;
+        const float dS = at * (dA - delta) / sqrt_d;
+#pragma unroll
+        for (int k = 0; k < KD; ++k) {
           dq[k] = fmaf(dS, kr[k], dq[k]);
-          atomicAdd(&dKs[t * D + d], dS * q[k]);
-          atomicAdd(&dVs[t * D + d], at * dz[k]);
+          dk[j][k] = fmaf(dS, q[k], dk[j][k]);
+          dv[j][k] = fmaf(at, dz[k], dv[j][k]);
+        }
+        if (t == s) {
+          // direct terms of the loss on the resampled K/V noises of the node's own row: 1/2 ||K - kx||^2 / sigma_k^2
+          // (same for V), once per final particle that descends from the node
+          const float mult = a.node_m[u];
+#pragma unroll
+          for (int k = 0; k < KD; ++k) {
+            const int d = lane + 32 * k;
+            if (d < D) {
+              const float tk = mult * c_k * (kr[k] - a.kx[(long long)bs * D + d]);
+              const float tv = mult * c_v * (vr[k] - a.vx[(long long)bs * D + d]);
+              dk[j][k] += tk; dv[j][k] += tv;
+              atomicAdd(a.dkx_sum + (long long)bs * D + d, -tk);
+              atomicAdd(a.dvx_sum + (long long)bs * D + d, -tv);
+            }
+          }
+        }
+      }
+      if (any) {
+#pragma unroll
+        for (int k = 0; k < KD; ++k) {
+          const int d = lane + 32 * k;
+          if (d < D) atomicAdd(a.dq_sum + (long long)bs * D + d, dq[k]);
         }
       }
     }
-    // direct terms of the loss on the resampled K/V noises of this node's own row: 1/2 ||K - kx||^2 / sigma_k^2
-    // (same for V), once per final particle that descends from the node
 #pragma unroll
-    for (int k = 0; k < KD; ++k) {
-      const int d = lane + 32 * k;
-      if (d < D) {
-        atomicAdd(a.dq_sum + (long long)bs * D + d, dq[k]);
-        const float tk = mult * c_k * (Kp[(long long)s * D + d] - a.kx[(long long)bs * D + d]);
-        const float tv = mult * c_v * (Vp[(long long)s * D + d] - a.vx[(long long)bs * D + d]);
-        atomicAdd(&dKs[s * D + d], tk); atomicAdd(&dVs[s * D + d], tv);
-        atomicAdd(&dKX[s * D + d], -tk); atomicAdd(&dVX[s * D + d], -tv);
+    for (int j = 0; j < BWD_TJ; ++j) {
+      const int t = tbase + wid + NWA * j;
+      if (t < S) {
+#pragma unroll
+        for (int k = 0; k < KD; ++k) {
+          const int d = lane + 32 * k;
+          if (d < D) {
+            atomicAdd(a.dk_sum + ((long long)b * S + t) * D + d, dk[j][k]);
+            atomicAdd(a.dv_sum + ((long long)b * S + t) * D + d, dv[j][k]);
+          }
+        }
       }
     }
-  }
-  __syncthreads();
-  for (int i = tid; i < S * D; i += BWD_ANT) {
-    const long long o = (long long)b * S * D + i;
-    atomicAdd(a.dk_sum + o, dKs[i]); atomicAdd(a.dv_sum + o, dVs[i]);
-    atomicAdd(a.dkx_sum + o, dKX[i]); atomicAdd(a.dvx_sum + o, dVX[i]);
   }
 }
 

@@ -413,7 +413,7 @@ size_t backward_ws(const smct_shape& s) {
   n += align_up(BPS * 2);                                       // anc
   n += 2 * align_up(((size_t)s.B * s.S + 1) * 4);               // node_cnt, node_off
   n += 2 * align_up(BPS * 4) + 2 * align_up(BPS * 2);           // node_bs, node_m, node_p, node_L
-  n += 2 * align_up(BPS * s.D * 4) + align_up(BPS * 2 * 4);     // Zm, dZm, stat
+  n += 3 * align_up(BPS * s.D * 4) + align_up(BPS * 2 * 4);     // Zm, dZm, Qm, stat
   n += 6 * align_up(BSD * 4);                                   // per-row sums
   n += align_up((size_t)BWD_NREP * l.total * 4) + align_up((size_t)l.total * 4);
   return n + 1024;
@@ -430,14 +430,12 @@ int launch_backward_t(const smct::BwdArgs& a, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
     SMCT_CUDA(cudaFuncSetAttribute(smct::bwd_dense_kernel<KD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    SMCT_CUDA(cudaFuncSetAttribute(smct::bwd_attn_bwd_kernel<KD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 205 * 1024));
     attr_set = true;
   }
   const long long ntiles = (nrows + smct::PT - 1) / smct::PT;
   smct::bwd_dense_kernel<KD><<<(int)std::min<long long>(ntiles, a.nrep), smct::NT, smem_d, st>>>(a);
   SMCT_LAUNCH_CHECK("bwd_dense_kernel");
-  const size_t smem_a = (size_t)4 * a.S * D * sizeof(float);
-  smct::bwd_attn_bwd_kernel<KD><<<a.B * smct::BWD_G, smct::BWD_ANT, smem_a, st>>>(a);
+  smct::bwd_attn_bwd_kernel<KD><<<a.B * smct::BWD_G, smct::BWD_ANT, 0, st>>>(a);
   SMCT_LAUNCH_CHECK("bwd_attn_bwd_kernel");
   return SMCT_OK;
 }
@@ -715,7 +713,7 @@ int smct_backward(const smct_shape* shape, const smct_params* params, const smct
   float* node_m = c.take<float>(BPS);
   unsigned short* node_p = c.take<unsigned short>(BPS);
   unsigned short* node_L = c.take<unsigned short>(BPS);
-  float* Zm = c.take<float>(BPS * D); float* dZm = c.take<float>(BPS * D); float* stat = c.take<float>(BPS * 2);
+  float* Zm = c.take<float>(BPS * D); float* dZm = c.take<float>(BPS * D); float* Qm = c.take<float>(BPS * D); float* stat = c.take<float>(BPS * 2);
   float* sums = c.take<float>(6 * BSD);   // contiguous: one memset
   float* rep = c.take<float>((size_t)BWD_NREP * lay.total);
   float* flat = c.take<float>((size_t)lay.total);
@@ -767,7 +765,7 @@ int smct_backward(const smct_shape* shape, const smct_params* params, const smct
   a.b_global0 = s.b_global0; a.seed = io->seed;
   a.x_in = io->x_in; a.X = X; a.xln = xln; a.q_ = q_; a.kx = kx; a.vx = vx;
   a.y = (const float*)io->y; a.eps = io->eps; a.p = *params; a.WzT = WzT; a.W1T = W1T; a.W2T = W2T;
-  a.K = io->K; a.V = io->V; a.i_out = io->i_out; a.anc = anc; a.node_off = node_off; a.node_bs = node_bs; a.node_p = node_p; a.node_L = node_L; a.node_m = node_m; a.Zm = Zm; a.dZm = dZm; a.stat = stat;
+  a.K = io->K; a.V = io->V; a.i_out = io->i_out; a.anc = anc; a.node_off = node_off; a.node_bs = node_bs; a.node_p = node_p; a.node_L = node_L; a.node_m = node_m; a.Zm = Zm; a.dZm = dZm; a.Qm = Qm; a.stat = stat;
   a.dq_sum = dq_sum; a.dk_sum = dk_sum; a.dv_sum = dv_sum; a.dxln_sum = dxln_sum; a.dkx_sum = dkx_sum; a.dvx_sum = dvx_sum;
   a.rep = rep; a.nrep = BWD_NREP; a.lay = lay;
   int rc;
