@@ -138,9 +138,9 @@ __device__ __forceinline__ void tile_gemm(const float* __restrict__ A, int lda, 
   }
 }
 
+// one timestep of one 32-particle tile (particles p0..p0+31 of sequence b); sm: step_smem_bytes() of shared memory
 template <int KD>
-__global__ void __launch_bounds__(NT) step_kernel(const StepArgs a) {
-  extern __shared__ float sm[];
+__device__ __forceinline__ void step_tile(const StepArgs& a, const int b, const int p0, float* sm) {
   const int D = a.D, Dp = D + 1, dff = a.dff, Fp = dff + 1, S = a.S, t = a.t;
   float* Zs = sm;
   float* Os = Zs + PT * Dp;
@@ -148,7 +148,6 @@ __global__ void __launch_bounds__(NT) step_kernel(const StepArgs a) {
   float* scr = Hs + (a.full_model ? PT * Fp : 0);
   float* red = scr + NW * 3 * D;  // 2*NW floats for loss partials
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int b = blockIdx.y, p0 = blockIdx.x * PT;
   const int np = min(PT, a.P - p0);
   const int Dh = D / a.H;
   const int GD = (D + 3) >> 2;
@@ -436,6 +435,12 @@ __global__ void __launch_bounds__(NT) step_kernel(const StepArgs a) {
   }
 }
 
+template <int KD>
+__global__ void __launch_bounds__(NT) step_kernel(const StepArgs a) {
+  extern __shared__ float sm[];
+  step_tile<KD>(a, blockIdx.y, blockIdx.x * PT, sm);
+}
+
 // ------------------------------------------------------------------------------------------
 // resample_kernel: one CTA per sequence
 // ------------------------------------------------------------------------------------------
@@ -452,11 +457,9 @@ struct ResampleArgs {
   int* i_out2;              // (B,P) optional second copy (user trace)
 };
 
-__global__ void __launch_bounds__(256) resample_kernel(const ResampleArgs a) {
-  extern __shared__ double cdf[];  // P doubles
-  __shared__ float scratch[32];
-  __shared__ double total_s;
-  const int b = blockIdx.x, P = a.P, tid = threadIdx.x;
+// draw of sequence b: cdf = P doubles of shared memory, scratch = 32 floats, total_s = 1 double (all shared)
+__device__ __forceinline__ void resample_seq(const ResampleArgs& a, const int b, double* cdf, float* scratch, double* total_sp) {
+  const int P = a.P, tid = threadIdx.x;
   const float* lw = a.logw + (long long)b * P;
   // 1. max over finite logits
   float m = -INFINITY;
@@ -487,10 +490,10 @@ __global__ void __launch_bounds__(256) resample_kernel(const ResampleArgs a) {
   if (tid == 0) {
     double run = 0.0;
     for (int p = 0; p < P; ++p) { run += cdf[p]; cdf[p] = run; }
-    total_s = run;
+    *total_sp = run;
   }
   __syncthreads();
-  const double total = total_s;
+  const double total = *total_sp;
   // 4. one draw per particle slot: upper_bound(cdf, u * total)
   for (int p = tid; p < P; p += blockDim.x) {
     const long long bp = (long long)b * P + p;
@@ -512,6 +515,13 @@ __global__ void __launch_bounds__(256) resample_kernel(const ResampleArgs a) {
     if (a.i_out) a.i_out[bp] = idx;
     if (a.i_out2) a.i_out2[bp] = idx;
   }
+}
+
+__global__ void __launch_bounds__(256) resample_kernel(const ResampleArgs a) {
+  extern __shared__ double cdf[];  // P doubles
+  __shared__ float scratch[32];
+  __shared__ double total_s;
+  resample_seq(a, blockIdx.x, cdf, scratch, &total_s);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -544,6 +554,99 @@ __global__ void __launch_bounds__(256) gather_kernel(const GatherArgs a) {
   } else {
     for (long long i = (long long)blockIdx.y * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.y * blockDim.x)
       dst[i] = src[i];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// seq_forward_kernel (SMCT_ALGO_STAGED_SEQ): the S x (step, draw, gather) loop of the staged path in ONE launch,
+// one CTA per sequence (sequences never interact; the particles of a sequence do).  Same device code as the staged
+// kernels, hence bit-identical results; made for the reference's own small shapes (P <= 128), where the staged path
+// is bound by ~5 launches per timestep.
+// ------------------------------------------------------------------------------------------
+struct SeqArgs {
+  StepArgs step;                 // step-independent fields (fill_step_common) + loss_sums
+  int attn_window, len_resampling, normalise, n_gather;
+  const float *xln, *q_, *k_, *v_;   // (B,S,D)
+  const void* y;                 // (B,S,Fy) f32 | (B,S) i32
+  const float* eps;              // optional (4,S,B,P,D)
+  const double* u;               // optional (S,B,P)
+  const int* i_forced;           // optional (S,B,P)
+  unsigned long long seed;
+  float *K0, *V0, *R0, *K2, *V2, *R2;   // io state and its ping-pong twin
+  float* logw_ws; int* idx_ws;   // (B,P) scratch
+  float *pred, *noise_q, *noise_z, *attn, *w, *logw_out;
+  int* i_out;
+};
+
+template <int KD>
+__global__ void __launch_bounds__(NT) seq_forward_kernel(const SeqArgs g) {
+  extern __shared__ float sm[];
+  __shared__ float scratch[32];
+  __shared__ double total_s;
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int B = g.step.B, P = g.step.P, S = g.step.S, D = g.step.D, H = g.step.H, Fy = g.step.Fy;
+  const size_t BPD = (size_t)B * P * D, BP = (size_t)B * P;
+  float *Kc, *Vc, *Rc, *Ka, *Va, *Ra;
+  if (g.n_gather % 2 == 0) { Kc = g.K0; Vc = g.V0; Rc = g.R0; Ka = g.K2; Va = g.V2; Ra = g.R2; }
+  else { Kc = g.K2; Vc = g.V2; Rc = g.R2; Ka = g.K0; Va = g.V0; Ra = g.R0; }
+  for (int t = 0; t < S; ++t) {
+    StepArgs a = g.step;
+    a.t = t;
+    a.s_lo = (g.attn_window >= 0 && t > g.attn_window) ? t - g.attn_window : 0;
+    a.xln = g.xln + (size_t)t * D; a.q_ = g.q_ + (size_t)t * D; a.k_ = g.k_ + (size_t)t * D; a.v_ = g.v_ + (size_t)t * D;
+    a.row_sb = (long long)S * D; a.row_sp = 0;
+    if (a.weights_mode == SMCT_WEIGHTS_GAUSSIAN) { a.y = (const float*)g.y + (size_t)t * Fy; a.y_sb = (long long)S * Fy; }
+    else { a.y = (const int*)g.y + t; a.y_sb = S; }
+    if (g.eps) {
+      a.eps_k = g.eps + ((size_t)0 * S + t) * BPD; a.eps_q = g.eps + ((size_t)1 * S + t) * BPD;
+      a.eps_v = g.eps + ((size_t)2 * S + t) * BPD; a.eps_z = g.eps + ((size_t)3 * S + t) * BPD;
+    }
+    a.seed = g.seed; a.t_rng = t;
+    a.K = Kc; a.V = Vc; a.R = Rc;
+    a.pred = g.pred ? g.pred + (size_t)t * Fy : nullptr; a.pred_st = (long long)S * Fy;
+    a.noise_q = g.noise_q ? g.noise_q + (size_t)t * D : nullptr;
+    a.noise_z = g.noise_z ? g.noise_z + (size_t)t * D : nullptr;
+    a.nz_st = (long long)S * D;
+    a.attn = g.attn ? g.attn + (size_t)t * S : nullptr;
+    a.attn_st_bp = (long long)H * S * S; a.attn_st_h = (long long)S * S;
+    a.logw = g.logw_ws;
+    for (int p0 = 0; p0 < P; p0 += PT) {
+      step_tile<KD>(a, b, p0, sm);
+      __syncthreads();
+    }
+    if (a.noise_on) {
+      ResampleArgs r;
+      r.B = B; r.P = P; r.normalise = g.normalise;
+      r.logw = g.logw_ws;
+      r.u = g.u ? g.u + (size_t)t * BP : nullptr;
+      r.i_forced = g.i_forced ? g.i_forced + (size_t)t * BP : nullptr;
+      r.seed = g.seed; r.b_global0 = a.b_global0; r.t_rng = t;
+      r.w_out = g.w ? g.w + t : nullptr; r.w_st = S;
+      r.logw_copy = g.logw_out ? g.logw_out + (size_t)t * BP : nullptr;
+      r.logits_out = nullptr;
+      r.i_out = g.idx_ws;
+      r.i_out2 = g.i_out ? g.i_out + (size_t)t * BP : nullptr;
+      resample_seq(r, b, reinterpret_cast<double*>(sm), scratch, &total_s);
+      __syncthreads();
+      if (g.len_resampling < 0 || t < g.len_resampling) {
+        // ancestor gather of this sequence: rows 0..t of K, V, R (transformer_utils.py:39-47)
+        const long long rowlen = (long long)(t + 1) * D, stride = (long long)S * D;
+        const long long n = (long long)P * rowlen;
+        const int* idx = g.idx_ws + (size_t)b * P;
+        for (int z = 0; z < 3; ++z) {
+          const float* src = (z == 0 ? Kc : (z == 1 ? Vc : Rc)) + (size_t)b * P * stride;
+          float* dst = (z == 0 ? Ka : (z == 1 ? Va : Ra)) + (size_t)b * P * stride;
+          for (long long i = tid; i < n; i += NT) {
+            const int m = (int)(i / rowlen);
+            const long long off = i - (long long)m * rowlen;
+            dst[(long long)m * stride + off] = src[(long long)idx[m] * stride + off];
+          }
+        }
+        float* tp;
+        tp = Kc; Kc = Ka; Ka = tp; tp = Vc; Vc = Va; Va = tp; tp = Rc; Rc = Ra; Ra = tp;
+        __syncthreads();
+      }
+    }
   }
 }
 

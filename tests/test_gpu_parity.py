@@ -365,3 +365,23 @@ def test_shards_reproduce_the_full_batch(algo):
             assert np.array_equal(part[k], full[k][b0:b1]), k
         sums += part["loss_sums"]
     assert np.allclose(sums[:5], full["loss_sums"][:5], rtol=1e-6)
+
+
+# ----------------------------------------------------------------------------- single-launch variant of the staged path
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_staged_seq_is_bit_identical_to_staged(name):
+    """SMCT_ALGO_STAGED_SEQ runs the staged device code in one launch (one CTA per sequence): identical bits, free-running,
+    with injected draws and with the device RNG; AUTO selects it for the small shapes."""
+    c = CASES[name]
+    cfg = c["cfg"]
+    p, x_in, y, eps, u = util.make_case(cfg, seed=21, sigma2=c["sigma2"], multi=c.get("multi", False))
+    want = ("i_out", "logw", "noise_K", "noise_V", "loss_sums", "attn")
+    for kw in (dict(eps=eps, u=u), dict(eps=None, u=None, seed=5, b_global0=3)):
+        ref = util.run_device(cfg, p, x_in, y, want=want, algo="staged", **kw)
+        for algo in ("staged_seq", "auto"):
+            got = util.run_device(cfg, p, x_in, y, want=want, algo=algo, **kw)
+            for k in ref:
+                if k == "loss_sums":   # fp64 atomics: the order of the adds differs between launches
+                    assert np.allclose(got[k], ref[k], rtol=1e-12, atol=0), k
+                else:
+                    assert np.array_equal(got[k], ref[k], equal_nan=True), (algo, k)
