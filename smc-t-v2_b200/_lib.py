@@ -103,9 +103,6 @@ def load(build_if_needed=True):
     if _lib is not None:
         return _lib
     path = _build.LIB
-    override = os.environ.get("SMCT_LIB_OVERRIDE")   # development: load an experimental build of the same sources
-    if override:
-        path, build_if_needed = override, False
     if build_if_needed:
         try:
             _build.build()

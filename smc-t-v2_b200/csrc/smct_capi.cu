@@ -369,16 +369,6 @@ int forward_fused(const smct_shape& s, const smct_params& pr, const smct_io& io,
   a.pred = io.pred; a.w = io.w; a.logw = io.logw; a.noise_q = io.noise_q; a.noise_z = io.noise_z;
   a.i_out = io.i_out; a.loss_sums = io.loss_sums;
   a.wtc = wtc;
-  {
-    static int pf_pro = -1, pf_dist = -1;
-    if (pf_pro < 0) {
-      const char* e1 = getenv("SMCT_PF_PRO");
-      const char* e2 = getenv("SMCT_PF_DIST");
-      pf_pro = e1 ? atoi(e1) : 0;
-      pf_dist = e2 ? atoi(e2) : 4;   // measured on B200 (C4, one wave): 69.8 ms without, 64.4 ms with distance 4
-    }
-    a.pf_pro = pf_pro; a.pf_dist = pf_dist;
-  }
   static bool attr_set = false;
   if (!attr_set) {
     SMCT_CUDA(cudaFuncSetAttribute(smct::fused_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

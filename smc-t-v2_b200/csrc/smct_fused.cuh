@@ -34,7 +34,6 @@ struct FusedArgs {
   float ln_eps, sigma_obs;
   long long b_global0;
   unsigned long long seed;
-  int pf_pro, pf_dist;               // L2 prefetch of history rows: blocks issued up front / distance inside the loop
   const float *xln, *q_, *k_, *v_;   // (B,S,64) particle-independent rows (rows_kernel)
   const float* y;                    // (B,S,Fy)
   const float* eps;                  // optional (4,S,B,P,64)

@@ -19,23 +19,6 @@
 #include <cuda_fp16.h>
 #include "smct_common.cuh"
 
-// development switches (A/B builds through scripts/dev/build_variants.sh)
-#ifndef SMCT_X_PREFETCH
-#define SMCT_X_PREFETCH 1
-#endif
-#ifndef SMCT_X_ACC3
-#define SMCT_X_ACC3 0
-#endif
-#ifndef SMCT_X_EARLYV
-#define SMCT_X_EARLYV 0
-#endif
-#ifndef SMCT_X_AVNEXT
-#define SMCT_X_AVNEXT 1
-#endif
-#ifndef SMCT_X_STCS
-#define SMCT_X_STCS 1
-#endif
-
 namespace smct {
 namespace attn {
 
@@ -72,7 +55,6 @@ __device__ __forceinline__ float ex2f(float x) {
 
 // L2 prefetch of the split K and V rows of one column (2 x 256 B), issued by the lane that opens the column
 __device__ __forceinline__ void prefetch_column(const unsigned char* Ks, const unsigned char* Vs, int slot, int row, int P) {
-  if (!SMCT_X_PREFETCH) return;
   const size_t off = ((size_t)slot * P + row) << 8;
   asm volatile("prefetch.global.L2 [%0];" ::"l"(Ks + off));
   asm volatile("prefetch.global.L2 [%0];" ::"l"(Ks + off + 128));
@@ -105,11 +87,6 @@ __device__ __forceinline__ void process_group(State& st, const uint2* cd, int nc
     const uint32_t rs = __shfl_sync(SMCT_FULL_MASK, d.x, 2 * c + (k & 1) + 8 * (k >> 1));
     vp[k] = Vs + (((size_t)(rs >> 16) * P + (rs & 0xFFFFu)) << 8) + 16 * r;
   }
-#if SMCT_X_EARLYV
-  uint4 vh[4];
-#pragma unroll
-  for (int k = 0; k < 4; ++k) vh[k] = *reinterpret_cast<const uint4*>(vp[k]);
-#endif
   float S[2][4];
 #pragma unroll
   for (int nt = 0; nt < 2; ++nt) {
@@ -122,26 +99,14 @@ __device__ __forceinline__ void process_group(State& st, const uint2* cd, int nc
     const uint32_t kh[4][2] = {{h0.x, h0.y}, {h0.z, h0.w}, {h1.x, h1.y}, {h1.z, h1.w}};
     const uint32_t km[4][2] = {{m0.x, m0.y}, {m0.z, m0.w}, {m1.x, m1.y}, {m1.z, m1.w}};
     S[nt][0] = S[nt][1] = S[nt][2] = S[nt][3] = 0.f;
-#if SMCT_X_ACC3
-    float Sb[4] = {0.f, 0.f, 0.f, 0.f};
-#endif
 #pragma unroll
     for (int j = 0; j < 4; ++j) {      // the Q fragments of one k-step at a time keep the live range short
       const uint4 qh4 = Qf[j * 32 + lane], qm4 = Qf[(4 + j) * 32 + lane];
       const uint32_t qh[4] = {qh4.x, qh4.y, qh4.z, qh4.w}, qm[4] = {qm4.x, qm4.y, qm4.z, qm4.w};
       mma16816(S[nt], qh, kh[j][0], kh[j][1]);
-#if SMCT_X_ACC3
-      mma16816(Sb, qm, kh[j][0], kh[j][1]);
-      mma16816(Sb, qh, km[j][0], km[j][1]);
-#else
       mma16816(S[nt], qm, kh[j][0], kh[j][1]);
       mma16816(S[nt], qh, km[j][0], km[j][1]);
-#endif
     }
-#if SMCT_X_ACC3
-#pragma unroll
-    for (int e = 0; e < 4; ++e) S[nt][e] += Sb[e];
-#endif
   }
   // mask: entry (row R, column j) counts iff lo_j <= R < hi_j
   float mx0 = -INFINITY, mx1 = -INFINITY;
@@ -184,17 +149,10 @@ __device__ __forceinline__ void process_group(State& st, const uint2* cd, int nc
   split2(S[1][2], S[1][3], Ph[3], Pm[3]);
 #pragma unroll
   for (int part = 0; part < 2; ++part) {
-#if SMCT_X_EARLYV
-    const uint4 va = part ? *reinterpret_cast<const uint4*>(vp[0] + 128) : vh[0];
-    const uint4 vb = part ? *reinterpret_cast<const uint4*>(vp[1] + 128) : vh[1];
-    const uint4 vc = part ? *reinterpret_cast<const uint4*>(vp[2] + 128) : vh[2];
-    const uint4 vd = part ? *reinterpret_cast<const uint4*>(vp[3] + 128) : vh[3];
-#else
     const uint4 va = *reinterpret_cast<const uint4*>(vp[0] + 128 * part);
     const uint4 vb = *reinterpret_cast<const uint4*>(vp[1] + 128 * part);
     const uint4 vc = *reinterpret_cast<const uint4*>(vp[2] + 128 * part);
     const uint4 vd = *reinterpret_cast<const uint4*>(vp[3] + 128 * part);
-#endif
     const uint32_t wa[4] = {va.x, va.y, va.z, va.w}, wb[4] = {vb.x, vb.y, vb.z, vb.w};
     const uint32_t wc[4] = {vc.x, vc.y, vc.z, vc.w}, wd[4] = {vd.x, vd.y, vd.z, vd.w};
 #pragma unroll

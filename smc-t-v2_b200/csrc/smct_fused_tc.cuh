@@ -6,10 +6,12 @@
 //     r' = h·W2[chunk, :]   -> tcgen05.mma accumulating over chunks  (cols 128..191)
 // Operands are fp16 (h,m) splits of power-of-two-scaled fp32 values (three MMA terms, see smct_tc.cuh) so that
 // the result keeps ~22 mantissa bits and the 1e-4 parity bar holds with margin.  Epilogues (bias, noise, residual, LayerNorm, relu,
-// re-split to bf16, output layer, log-weight) are done by all 16 warps straight from TMEM (tcgen05.ld):
+// re-split to fp16, output layer, log-weight) are done by all 16 warps straight from TMEM (tcgen05.ld):
 // warp w owns TMEM lanes 32*(w%4).. (rows) and columns 16*(w/4).. of the 64-wide accumulator.
-// Weight blocks (bf16 h,m, pre-arranged in the operand layout by tc_weight_prep_kernel) stream from L2 into
-// shared memory with cp.async, double-buffered per FFN chunk.
+// Weight blocks (fp16 h,m, pre-arranged in the operand layout by tc_weight_prep_kernel): W1 stays resident in shared
+// memory, Wz and the W2 chunks stream from L2 with cp.async through two buffers.  The four first FFN GEMMs are issued
+// at once into four TMEM ranges, so the relu/split epilogue of a chunk overlaps the tensor-core work of the others.
+// The attention over the genealogy runs on warp-level MMAs (smct_fused_attn.cuh).
 #pragma once
 #include "smct_fused.cuh"
 #include "smct_tc.cuh"
@@ -46,21 +48,6 @@ __device__ __forceinline__ void cp_async_wait_1() { asm volatile("cp.async.wait_
 __device__ __forceinline__ void copy_block_async(unsigned char* dst, const unsigned char* src, int bytes) {
   for (int i = threadIdx.x; i < bytes / 16; i += FNT) cp_async16(dst + 16 * i, src + 16 * i);
 }
-__device__ __forceinline__ void prefetch_l2(const void* p) {
-  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-}
-// lane l4 of a particle prefetches one 256-byte row (two lines) of the slot pair starting at s: lanes 0,1 -> K,V of
-// slot s, lanes 2,3 -> K,V of slot s+1
-__device__ __forceinline__ void prefetch_rows(const float* Kb, const float* Vb, int slot, int row, int P, int l4) {
-  const float* base = ((l4 & 1) ? Vb : Kb) + (size_t)((uint32_t)(slot * P + row) * FD);
-  prefetch_l2(base);
-  prefetch_l2(base + 32);
-}
-__device__ __forceinline__ float ex2_approx(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float v[16]) {
   uint32_t r[16];
@@ -74,30 +61,6 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float v[16]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// one online-softmax update over a block of FSB slots (scores already in the log2 domain)
-__device__ __forceinline__ void softmax_block(const float sc[FSB], const float4 vr[FSB][4], float& m, float& l,
-                                              float4 zacc[4]) {
-  float mn = m;
-#pragma unroll
-  for (int j = 0; j < FSB; ++j) mn = fmaxf(mn, sc[j]);
-  const float corr = ex2_approx(m - mn);
-  float pj[FSB], psum = 0.f;
-#pragma unroll
-  for (int j = 0; j < FSB; ++j) { pj[j] = ex2_approx(sc[j] - mn); psum += pj[j]; }
-  l = fmaf(l, corr, psum);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    float4 zz = make_float4(zacc[i].x * corr, zacc[i].y * corr, zacc[i].z * corr, zacc[i].w * corr);
-#pragma unroll
-    for (int j = 0; j < FSB; ++j) {
-      zz.x = fmaf(pj[j], vr[j][i].x, zz.x); zz.y = fmaf(pj[j], vr[j][i].y, zz.y);
-      zz.z = fmaf(pj[j], vr[j][i].z, zz.z); zz.w = fmaf(pj[j], vr[j][i].w, zz.w);
-    }
-    zacc[i] = zz;
-  }
-  m = mn;
 }
 
 __global__ void __launch_bounds__(FNT, 1) fused_tc_forward_kernel(const FusedArgs a) {
@@ -223,13 +186,9 @@ __global__ void __launch_bounds__(FNT, 1) fused_tc_forward_kernel(const FusedArg
           const float qs = sm.hdr.s_q;
           *reinterpret_cast<float4*>(&sm.Os[pl * FLD + d0]) = make_float4(qo[0] * qs, qo[1] * qs, qo[2] * qs, qo[3] * qs);
           if (act) {
-#if SMCT_X_STCS   // fp32 rows: read again only by the final pass
+            // fp32 rows: read again only by the final pass
             __stcs(reinterpret_cast<float4*>(Kb + prow + d0), make_float4(ko[4 * i], ko[4 * i + 1], ko[4 * i + 2], ko[4 * i + 3]));
             __stcs(reinterpret_cast<float4*>(Vb + prow + d0), make_float4(vo[4 * i], vo[4 * i + 1], vo[4 * i + 2], vo[4 * i + 3]));
-#else
-            *reinterpret_cast<float4*>(Kb + prow + d0) = make_float4(ko[4 * i], ko[4 * i + 1], ko[4 * i + 2], ko[4 * i + 3]);
-            *reinterpret_cast<float4*>(Vb + prow + d0) = make_float4(vo[4 * i], vo[4 * i + 1], vo[4 * i + 2], vo[4 * i + 3]);
-#endif
             if (a.noise_q) __stcs(reinterpret_cast<float4*>(a.noise_q + lrow + d0), make_float4(nq[0], nq[1], nq[2], nq[3]));
           }
         }
@@ -295,14 +254,9 @@ __global__ void __launch_bounds__(FNT, 1) fused_tc_forward_kernel(const FusedArg
         uint2 av_next = make_uint2(0u, 0u);
         if (4 * u_first < t) av_next = *reinterpret_cast<const uint2*>(Arow + 4 * u_first);
         for (int u = u_first; u <= (t >> 2); u += 2) {
-#if SMCT_X_AVNEXT
           const uint2 av = av_next;
           av_next = make_uint2(0u, 0u);
           if (4 * (u + 2) < t) av_next = *reinterpret_cast<const uint2*>(Arow + 4 * (u + 2));   // requested one unit ahead
-#else
-          uint2 av = make_uint2(0u, 0u);
-          if (4 * u < t) av = *reinterpret_cast<const uint2*>(Arow + 4 * u);
-#endif
           if (4 * u >= s_lo && 4 * u + 3 < t) {
             const uint32_t x0 = __shfl_sync(SMCT_FULL_MASK, av.x, 0), y0 = __shfl_sync(SMCT_FULL_MASK, av.y, 0);
             if (__all_sync(SMCT_FULL_MASK, av.x == x0 && av.y == y0)) {
