@@ -37,14 +37,20 @@ def _categorical(logits, u):
 
 
 def forward(cfg, p, x_in, y, eps=None, u=None, generator=None, i_forced=None):
-    """cfg: oracle Config (gaussian weights, linear input).  p: dict of torch CPU fp32 tensors.
-    x_in (B,S,F_x), y (B,S,F_y) torch CPU.  eps (4,S,B,P,D) / u (S,B,P) optional injected draws."""
+    """cfg: oracle Config.  p: dict of torch CPU fp32 tensors.
+    x_in (B,S,F_x) floats | (B,S) tokens (input_mode embedding); y (B,S,F_y) floats | (B,S) class ids (classification
+    weights).  eps (4,S,B,P,D) / u (S,B,P) optional injected draws."""
     B, P, S, D, H = cfg.B, cfg.P, cfg.S, cfg.D, cfg.H
     Dh = D // H
     # get_encoded_input: tile first, then project (SMC_Transformer.py:166-172)
-    inp = x_in.reshape(B, 1, S, cfg.F_x).repeat(1, P, 1, 1)
-    X = (inp @ p["W_in"] + p["b_in"]) * math.sqrt(D)                     # (B,P,S,D)
-    tgt = y.reshape(B, 1, S, cfg.F_y).repeat(1, P, 1, 1)
+    classification = cfg.weights == "classification"
+    if cfg.input_mode == "embedding":                                    # checkout: Embedding(tokens) * sqrt(D) (:56,:170)
+        inp = x_in.reshape(B, 1, S).repeat(1, P, 1).long()
+        X = p["W_in"][inp] * math.sqrt(D)
+    else:                                                                # regression era (pyc): Dense projection_layer_ts
+        inp = x_in.reshape(B, 1, S, cfg.F_x).repeat(1, P, 1, 1)
+        X = (inp @ p["W_in"] + p["b_in"]) * math.sqrt(D)                 # (B,P,S,D)
+    tgt = y.reshape(B, 1, S, -1).repeat(1, P, 1, 1)                       # (B,P,S,F_y) floats | (B,P,S,1) class ids
     K = torch.zeros(B, P, S, D)
     V = torch.zeros(B, P, S, D)
     R = torch.zeros(B, P, S, D)
@@ -96,9 +102,13 @@ def forward(cfg, p, x_in, y, eps=None, u=None, generator=None, i_forced=None):
             r = z
         pred = r @ p["Wo"]
         R = torch.cat([R[:, :, :t], r, R[:, :, t + 1:]], dim=2)
-        diff = yt - pred
-        logw = (-0.5 * (diff * diff).sum(-1).squeeze(-1)) / cfg.sigma_obs         # (B,P)
-        logw = logw - torch.logsumexp(logw, dim=1, keepdim=True)
+        if classification:                                                         # compute_w_classification (:78-84):
+            probs = torch.softmax(pred.squeeze(2), dim=-1)                         # the probabilities go in as logits (:165-166)
+            logw = torch.gather(probs, -1, yt.reshape(B, P, 1).long()).squeeze(-1)
+        else:
+            diff = yt - pred
+            logw = (-0.5 * (diff * diff).sum(-1).squeeze(-1)) / cfg.sigma_obs     # (B,P)
+            logw = logw - torch.logsumexp(logw, dim=1, keepdim=True)
         logw = logw.detach()                                                       # w, i_t are stop_gradient (:167)
         if i_forced is not None:
             i_t = i_forced[t].long()
@@ -111,7 +121,7 @@ def forward(cfg, p, x_in, y, eps=None, u=None, generator=None, i_forced=None):
             K, V, R = torch.split(KVR, D, dim=-1)
             K, V, R = K.contiguous(), V.contiguous(), R.contiguous()
         r_list.append(r)
-        w_list.append(torch.exp(logw))
+        w_list.append(logw if classification else torch.exp(logw))
         i_list.append(i_t)
         nq_list.append(noise_q)
         nz_list.append(noise_z)
@@ -135,8 +145,11 @@ def loss_and_grads(cfg, p_np, x_in, y, eps, i_forced, variant="pyc"):
     old = torch.get_default_dtype()
     torch.set_default_dtype(torch.float64)
     try:
-        out = forward(cfg, tp, torch.as_tensor(np.asarray(x_in, np.float64)), torch.as_tensor(np.asarray(y, np.float64)),
-                      eps=torch.as_tensor(np.asarray(eps, np.float64)), i_forced=torch.as_tensor(np.asarray(i_forced)))
+        tx = torch.as_tensor(np.asarray(x_in)) if cfg.input_mode == "embedding" else torch.as_tensor(np.asarray(x_in, np.float64))
+        classification = cfg.weights == "classification"
+        ty = torch.as_tensor(np.asarray(y)) if classification else torch.as_tensor(np.asarray(y, np.float64))
+        out = forward(cfg, tp, tx, ty, eps=torch.as_tensor(np.asarray(eps, np.float64)),
+                      i_forced=torch.as_tensor(np.asarray(i_forced)))
         B, S = cfg.B, cfg.S
         tot = 0.0
         for n, lv in (("noise_K_resampled", "logvar_k"), ("noise_q", "logvar_q"), ("noise_V_resampled", "logvar_v"),
@@ -146,8 +159,13 @@ def loss_and_grads(cfg, p_np, x_in, y, eps, i_forced, variant="pyc"):
                 D = out[n].shape[-1]
                 part = part + 0.5 * D * math.log(2 * math.pi) + 0.5 * D * tp[lv]
             tot = tot + part.mean()
-        diff = torch.as_tensor(np.asarray(y, np.float64)).reshape(B, 1, S, cfg.F_y) - out["pred_resampl"]
-        loss = tot + (0.5 / cfg.sigma_obs) * diff.square().sum(-1).mean()
+        if classification:   # compute_classic_loss (SMC_Transformer.py:148-164): sparse CE of the resampled logits
+            pr = out["pred_resampl"]
+            tgt = ty.reshape(B, 1, S).repeat(1, cfg.P, 1).long()
+            loss = tot + torch.nn.functional.cross_entropy(pr.reshape(-1, pr.shape[-1]), tgt.reshape(-1))
+        else:
+            diff = ty.reshape(B, 1, S, cfg.F_y) - out["pred_resampl"]
+            loss = tot + (0.5 / cfg.sigma_obs) * diff.square().sum(-1).mean()
         names = list(tp)
         grads = torch.autograd.grad(loss, [tp[n] for n in names], allow_unused=True)
     finally:

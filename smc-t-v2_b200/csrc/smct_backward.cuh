@@ -41,13 +41,13 @@ struct GradLayout {
 };
 
 struct BwdArgs {
-  int B, P, S, D, dff, Fy, Fx, attn_window, len_resampling, input_mode;
+  int B, P, S, D, dff, Fy, Fx, attn_window, len_resampling, input_mode, weights_mode;
   float ln_eps, sigma_obs, inv_n, sqrtD;
   long long b_global0;
   unsigned long long seed;
   const void* x_in;
   const float *X, *xln, *q_, *kx, *vx;   // (B,S,D) rows (rows_kernel)
-  const float* y;                         // (B,S,Fy)
+  const void* y;                          // (B,S,Fy) f32 (gaussian) | (B,S) i32 class ids (classification)
   const float* eps;                       // optional (4,S,B,P,D)
   smct_params p;
   const float *WzT, *W1T, *W2T;           // transposed weights
@@ -342,12 +342,30 @@ __global__ void __launch_bounds__(NT) bwd_dense_kernel(const BwdArgs a) {
         dr[k] = 0.f;
       }
       if (pl < np) {
+        // d loss / d pred: gaussian 1/2||y - pred||^2/Sigma_obs (regression era) | sparse cross-entropy of the logits
+        // (compute_classic_loss, SMC_Transformer.py:148-164); both averaged over (b,p,s) and scaled by the multiplicity
+        const bool ce = a.weights_mode == SMCT_WEIGHTS_CLASSIFICATION;
+        float mx = -INFINITY, se = 0.f;
+        int ytok = 0;
+        if (ce) {
+          ytok = ((const int*)a.y)[rbs[pl]];
+          for (int f = 0; f < Fy; ++f) {
+            float part = 0.f;
+#pragma unroll
+            for (int k = 0; k < KD; ++k) { const int d = lane + 32 * k; if (d < D) part = fmaf(r[k], __ldg(a.p.Wo + (long long)d * Fy + f), part); }
+            const float pr = warp_sum(part);
+            const float mn = fmaxf(mx, pr);
+            se = se * expf(mx - mn) + expf(pr - mn);
+            mx = mn;
+          }
+        }
         for (int f = 0; f < Fy; ++f) {
           float part = 0.f;
 #pragma unroll
           for (int k = 0; k < KD; ++k) { const int d = lane + 32 * k; if (d < D) part = fmaf(r[k], __ldg(a.p.Wo + (long long)d * Fy + f), part); }
           const float pr = warp_sum(part);
-          const float dpred = (pr - a.y[(long long)rbs[pl] * Fy + f]) * (c_obs * rm[pl]);   // m final particles share this node
+          const float dpred = ce ? (expf(pr - mx) / se - (f == ytok ? 1.f : 0.f)) * (a.inv_n * rm[pl])
+                                 : (pr - ((const float*)a.y)[(long long)rbs[pl] * Fy + f]) * (c_obs * rm[pl]);   // m final particles share this node
 #pragma unroll
           for (int k = 0; k < KD; ++k) {
             const int d = lane + 32 * k;

@@ -419,9 +419,11 @@ smct::GradLayout make_layout(const smct_shape& s) {
 constexpr int BWD_NREP = 296;
 
 int check_backward_shape(const smct_shape& s) {
-  if (s.H != 1 || !s.full_model || !s.noise_on || s.weights_mode != SMCT_WEIGHTS_GAUSSIAN || s.logvar_dim != 1 ||
-      s.noise_z_mode != SMCT_NOISE_Z_PYC)
-    return fail(SMCT_ERR_UNSUPPORTED, "backward supports: gaussian weights, 1 head, full model, scalar log-variances, noise_z_mode pyc");
+  // noise_z_mode checkout (noise_z = z - z_, self_attention_SMC.py:190) makes the noise_z loss term of EVERY per-step
+  // particle depend on the parameters, including particles that do not survive to the final genealogy: that term is
+  // outside the path-wise formulation (which sees the final lineages only)
+  if (s.H != 1 || !s.full_model || !s.noise_on || s.logvar_dim != 1 || s.noise_z_mode != SMCT_NOISE_Z_PYC)
+    return fail(SMCT_ERR_UNSUPPORTED, "backward supports: 1 head, full model, noise on, scalar log-variances, noise_z_mode pyc");
   if (s.D > 128) return fail(SMCT_ERR_UNSUPPORTED, "backward: d_model %d > 128", s.D);
   if ((long long)s.S * s.D > 12800) return fail(SMCT_ERR_UNSUPPORTED, "backward: S*d_model %lld > 12800", (long long)s.S * s.D);
   if (s.P > 12288) return fail(SMCT_ERR_UNSUPPORTED, "backward: particles %d > 12288", s.P);
@@ -788,11 +790,11 @@ int smct_backward(const smct_shape* shape, const smct_params* params, const smct
   smct::BwdArgs a;
   memset(&a, 0, sizeof(a));
   a.B = B; a.P = P; a.S = S; a.D = D; a.dff = s.dff; a.Fy = s.F_y; a.Fx = s.F_x; a.attn_window = s.attn_window;
-  a.len_resampling = s.len_resampling; a.input_mode = s.input_mode;
+  a.len_resampling = s.len_resampling; a.input_mode = s.input_mode; a.weights_mode = s.weights_mode;
   a.ln_eps = s.ln_eps; a.sigma_obs = s.sigma_obs; a.inv_n = inv_n; a.sqrtD = sqrtf((float)D);
   a.b_global0 = s.b_global0; a.seed = io->seed;
   a.x_in = io->x_in; a.X = X; a.xln = xln; a.q_ = q_; a.kx = kx; a.vx = vx;
-  a.y = (const float*)io->y; a.eps = io->eps; a.p = *params; a.WzT = WzT; a.W1T = W1T; a.W2T = W2T;
+  a.y = io->y; a.eps = io->eps; a.p = *params; a.WzT = WzT; a.W1T = W1T; a.W2T = W2T;
   a.K = io->K; a.V = io->V; a.i_out = io->i_out; a.anc = anc; a.node_off = node_off; a.node_bs = node_bs; a.node_p = node_p; a.node_L = node_L; a.node_m = node_m; a.Zm = Zm; a.dZm = dZm; a.Qm = Qm; a.stat = stat;
   a.dq_sum = dq_sum; a.dk_sum = dk_sum; a.dv_sum = dv_sum; a.dxln_sum = dxln_sum; a.dkx_sum = dkx_sum; a.dvx_sum = dvx_sum;
   a.rep = rep; a.nrep = BWD_NREP; a.lay = lay;

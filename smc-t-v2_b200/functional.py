@@ -337,7 +337,7 @@ def backward(shape: SmctShape, params: Dict[str, torch.Tensor], x_in: torch.Tens
     io = SmctIO()
     x_dtype = torch.int32 if shape.input_mode == INPUT["embedding"] else torch.float32
     io.x_in = _ptr(x_in, x_dtype, "x_in")
-    io.y = _ptr(y, torch.float32, "y")
+    io.y = _ptr(y, torch.int32 if shape.weights_mode == WEIGHTS["classification"] else torch.float32, "y")
     io.eps = _ptr(eps, torch.float32, "eps")
     io.seed = int(seed)
     io.K = _ptr(fwd["K"], torch.float32, "K")

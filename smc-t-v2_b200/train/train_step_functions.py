@@ -37,12 +37,11 @@ def train_step_SMC_T(inputs, targets, smc_transformer, optimizer, it, attention_
                                                    num_particles=smc_transformer.cell.num_particles,
                                                    attention_mask=attention_mask)
     if optimizer is not None:
-        if not regression:
-            raise NotImplementedError("gradients are built for the regression (gaussian-weight) SMC-T; the classification "
-                                      "checkout variant is forward-only")
         rank, world = D.world()
         B, P, S = preds.shape[0], preds.shape[1], preds.shape[2]
-        grads = compute_gradients(smc_transformer, inputs, targets, inv_n=1.0 / (float(B) * world * P * S))
+        # regression era (pyc): no log-determinant terms; the nlp checkout: full -log N terms + sparse cross-entropy
+        grads = compute_gradients(smc_transformer, inputs, targets, inv_n=1.0 / (float(B) * world * P * S),
+                                  loss_variant="pyc" if regression else "checkout")
         names = sorted(grads)
         if world > 1:
             flat = torch.cat([grads[n].reshape(-1) for n in names])

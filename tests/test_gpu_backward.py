@@ -17,6 +17,10 @@ BWD_CASES = {
     "d64_p70": O.Config(B=2, P=70, S=10, D=64, dff=256, F_x=2, F_y=2, noise_z_mode="pyc"),
     "window_stop": O.Config(B=2, P=33, S=9, D=16, dff=24, attn_window=3, len_resampling=5, noise_z_mode="pyc"),
     "d128": O.Config(B=1, P=20, S=6, D=128, dff=64, noise_z_mode="pyc"),
+    # the nlp checkout's observation model: Embedding input, softmax(pred)[y] weights, sparse cross-entropy
+    # (with the post-projection noise_z of the regression era: the checkout's z - z_ quirk is forward-only)
+    "classification": O.Config(B=3, P=12, S=9, D=16, dff=16, F_x=30, F_y=30, weights="classification",
+                               input_mode="embedding", noise_z_mode="pyc"),
 }
 
 
