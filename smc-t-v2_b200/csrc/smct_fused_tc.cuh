@@ -370,7 +370,7 @@ __global__ void __launch_bounds__(FNT, 1) fused_tc_forward_kernel(const FusedArg
       tc::fence_after_sync();
 
       // =========================== phase B: dense tile on the tensor cores ===========================
-      if (tid == 0) {
+      if (wid == 0 && tc::elect_one()) {
         tc::mma_block_bf16x3(tD_z, tc::smem_u32(sm.ZH), tc::smem_u32(sm.Ws[0]), tc::B_PART_BYTES, idesc, false);
         tc::commit(&sm.mbar_z);
       }
@@ -451,7 +451,7 @@ __global__ void __launch_bounds__(FNT, 1) fused_tc_forward_kernel(const FusedArg
       tc::fence_after_sync();
       // ---- FFN: the four first GEMMs (o · W1 chunk, W1 resident) are issued at once into four TMEM ranges; the relu /
       //      split epilogue of chunk c then overlaps the tensor-core work of the later chunks and of the second GEMMs ----
-      if (tid == 0) {
+      if (wid == 0 && tc::elect_one()) {
         for (int c = 0; c < FF / FD; ++c) {
           tc::mma_block_bf16x3(tD_h + FD * c, tc::smem_u32(sm.Ob), tc::smem_u32(sm.W1all[c]), tc::B_PART_BYTES, idesc, false);
           tc::commit(&sm.mbar_h[c]);
@@ -481,7 +481,7 @@ __global__ void __launch_bounds__(FNT, 1) fused_tc_forward_kernel(const FusedArg
         tc::fence_before_sync();
         __syncthreads();
         tc::fence_after_sync();
-        if (tid == 0) {
+        if (wid == 0 && tc::elect_one()) {
           tc::mma_block_bf16x3(tD_r, tc::smem_u32(sm.ZH), tc::smem_u32(sm.Ws[(c + 1) & 1]), tc::B_PART_BYTES, idesc, c > 0);
           tc::commit(&sm.mbar_r);
         }

@@ -68,19 +68,36 @@ __device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t desc_a, uint64
 
 // D[128 x N] (+)= A[128 x 64] * B[N x 64]^T with the three-term bf16 split.  One thread issues.
 // a_base / b_base: shared addresses of the h part; the m part follows at +A_PART_BYTES / +b_part_bytes.
+// The start-address field of a descriptor is (address >> 4) in bits [0,14): with < 256 KB of shared memory an offset
+// can simply be added to a base descriptor (no carry into the other fields), which keeps the single issuing thread short.
 __device__ __forceinline__ void mma_block_bf16x3(uint32_t tmem_d, uint32_t a_base, uint32_t b_base, uint32_t b_part_bytes,
                                                  uint32_t idesc, bool accumulate) {
+  const uint64_t da0 = make_desc(a_base), db0 = make_desc(b_base);
   const uint32_t a_off[3] = {0u, A_PART_BYTES, 0u};
   const uint32_t b_off[3] = {0u, 0u, b_part_bytes};
 #pragma unroll
   for (int term = 0; term < 3; ++term) {
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) {
-      const uint64_t da = make_desc(a_base + a_off[term] + 256u * ks);
-      const uint64_t db = make_desc(b_base + b_off[term] + 256u * ks);
+      const uint64_t da = da0 + (uint64_t)((a_off[term] + 256u * ks) >> 4);
+      const uint64_t db = db0 + (uint64_t)((b_off[term] + 256u * ks) >> 4);
       mma_f16(tmem_d, da, db, idesc, (accumulate || term > 0 || ks > 0) ? 1u : 0u);
     }
   }
+}
+
+// one lane of a converged warp (elect.sync): the MMA issue sites branch on the WARP and elect inside, so the compiler
+// sees a uniform branch instead of a divergent `tid == 0`
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
 }
 
 __device__ __forceinline__ void commit(uint64_t* mbar) {
