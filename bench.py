@@ -356,6 +356,10 @@ def run_b200(args):
                        "parallelism": "batch-sharded replicas, no collective in the forward"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic(algo_used, wl), "peak_source": peak_src,
+                         # the fused path avoids most of the algorithmic bytes (path storage instead of the ancestor gather):
+                         # frac > 1 is expected; this is the DRAM bandwidth the ncu-measured traffic of one launch amounts to
+                         "traffic_frac_of_peak": (None if ncu_traffic(algo_used, wl) is None or min(chunk, B) != 444 else
+                                                  ncu_traffic(algo_used, wl) / (fwd_ms * 1e-3) / 1e9 / peak),
                          "algorithmic_bytes_per_particle_step": bpp, "algorithmic_bytes_per_launch": alg_bytes_per_launch,
                          "launch": "one smct_forward call over one chunk (%.1f ms avg, CUDA events)" % fwd_ms},
             "cpu_baseline": cpu,
