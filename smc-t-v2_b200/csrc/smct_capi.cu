@@ -343,7 +343,7 @@ int forward_fused(const smct_shape& s, const smct_params& pr, const smct_io& io,
   if (io.loss_sums) SMCT_CUDA(cudaMemsetAsync(io.loss_sums, 0, 8 * sizeof(double), st));
   if (use_tc) {
     smct::TcAttnPrep ap{pr.Wq, pr.bq, pr.Wk, pr.bk, pr.Wv, pr.bv, pr.logvar_q, pr.logvar_k, pr.logvar_v, s.logvar_dim};
-    smct::tc_weight_prep_kernel<<<1, 1024, 0, st>>>(pr.Wz, pr.W1, pr.W2, pr.b1, pr.ln1_g, pr.ln1_b, smct::FF, wtc, ap);
+    smct::tc_weight_prep_kernel<<<1, 1024, 0, st>>>(pr.Wz, pr.W1, pr.W2, pr.b1, pr.ln1_g, pr.ln1_b, s.dff, wtc, ap);
     SMCT_LAUNCH_CHECK("tc_weight_prep_kernel");
   }
 
@@ -358,7 +358,7 @@ int forward_fused(const smct_shape& s, const smct_params& pr, const smct_io& io,
 
   smct::FusedArgs a;
   memset(&a, 0, sizeof(a));
-  a.B = B; a.P = P; a.S = S; a.Sa = Sa; a.Fy = s.F_y;
+  a.B = B; a.P = P; a.S = S; a.Sa = Sa; a.Fy = s.F_y; a.dff = s.dff;
   a.attn_window = s.attn_window; a.len_resampling = s.len_resampling; a.noise_z_mode = s.noise_z_mode;
   a.logvar_dim = s.logvar_dim; a.ln_eps = s.ln_eps; a.sigma_obs = s.sigma_obs;
   a.b_global0 = s.b_global0; a.seed = io.seed;

@@ -21,7 +21,7 @@
 namespace smct {
 
 constexpr int FD = 64;        // d_model handled by the fused kernel
-constexpr int FF = 256;       // dff
+constexpr int FF = 256;       // largest dff (the kernels serve dff = 64, 128, 192, 256: chunks of 64 hidden units)
 constexpr int FNT = 512;      // threads per CTA
 constexpr int FTILE = 128;    // particles per tile (4 lanes each)
 constexpr int FLD = 68;       // row stride (floats) of the activation tiles in shared memory
@@ -29,7 +29,7 @@ constexpr int FPMAX = 1024;   // max particles
 constexpr int FSB = 2;        // slots per online-softmax block
 
 struct FusedArgs {
-  int B, P, S, Sa, Fy;
+  int B, P, S, Sa, Fy, dff;
   int attn_window, len_resampling, noise_z_mode, logvar_dim;
   float ln_eps, sigma_obs;
   long long b_global0;
@@ -106,14 +106,14 @@ __device__ __forceinline__ void gemm_tile(const float* __restrict__ As, const fl
 }
 
 // weight block `blk` of the per-tile sequence: 0 = Wz, 1+2c = W1[:, 64c:64c+64], 2+2c = W2[64c:64c+64, :]
-__device__ __forceinline__ void wblock_issue(const smct_params& p, int blk, int tid, float4 wr[2]) {
+__device__ __forceinline__ void wblock_issue(const smct_params& p, int dff, int blk, int tid, float4 wr[2]) {
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
     const int e = tid + h * FNT;          // float4 index within the 64x64 block (1024 float4)
     const int r = e >> 4, c4 = e & 15;    // row, float4 column
     const float* src;
     if (blk == 0) src = p.Wz + r * FD + 4 * c4;
-    else if (blk & 1) src = p.W1 + r * FF + ((blk - 1) >> 1) * FD + 4 * c4;
+    else if (blk & 1) src = p.W1 + r * dff + ((blk - 1) >> 1) * FD + 4 * c4;
     else src = p.W2 + (((blk - 2) >> 1) * FD + r) * FD + 4 * c4;
     wr[h] = __ldg(reinterpret_cast<const float4*>(src));
   }
@@ -272,7 +272,7 @@ __global__ void __launch_bounds__(FNT, 1) fused_forward_kernel(const FusedArgs a
       const int q0 = g * FTILE;
       const int np = min(FTILE, P - q0);
       float4 wr[2];
-      wblock_issue(a.p, 0, tid, wr);   // Wz block travels while the tile does attention
+      wblock_issue(a.p, a.dff, 0, tid, wr);   // Wz block travels while the tile does attention
 
       // =========================== phase A: noise, slot-t rows, attention ===========================
       {
@@ -395,7 +395,7 @@ __global__ void __launch_bounds__(FNT, 1) fused_forward_kernel(const FusedArgs a
       // =========================== phase B: dense tile pipeline ===========================
       float acc[4][4];
       // ---- z = dense(z_) + noise ; o_pre = z + x ----
-      wblock_issue(a.p, 1, tid, wr);
+      wblock_issue(a.p, a.dff, 1, tid, wr);
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -440,9 +440,9 @@ __global__ void __launch_bounds__(FNT, 1) fused_forward_kernel(const FusedArgs a
       for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc2[i][j] = 0.f;
-      for (int c = 0; c < FF / FD; ++c) {
+      for (int c = 0; c < a.dff / FD; ++c) {
         // GEMM1 chunk c : weight block 1+2c lives in WB[1]; prefetch block 2+2c
-        wblock_issue(a.p, 2 + 2 * c, tid, wr);
+        wblock_issue(a.p, a.dff, 2 + 2 * c, tid, wr);
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -458,8 +458,8 @@ __global__ void __launch_bounds__(FNT, 1) fused_forward_kernel(const FusedArgs a
         wblock_commit(sm.WB[0], tid, wr);
         __syncthreads();
         // GEMM2 chunk c : weight block 2+2c lives in WB[0]; prefetch block 1+2(c+1) (or nothing)
-        const bool more = (c + 1) < FF / FD;
-        if (more) wblock_issue(a.p, 1 + 2 * (c + 1), tid, wr);
+        const bool more = (c + 1) < a.dff / FD;
+        if (more) wblock_issue(a.p, a.dff, 1 + 2 * (c + 1), tid, wr);
         gemm_tile(sm.Hs, sm.WB[0], acc2, tx, ty);
         if (more) wblock_commit(sm.WB[1], tid, wr);
         __syncthreads();
@@ -617,7 +617,7 @@ __global__ void __launch_bounds__(256) materialize_final_kernel(const MatArgs a)
 inline size_t fused_align(size_t x) { return (x + 255) / 256 * 256; }
 
 inline bool fused_supported(const smct_shape& s, const smct_io& io) {
-  return s.D == FD && s.dff == FF && s.H == 1 && s.full_model == 1 && s.noise_on == 1 &&
+  return s.D == FD && s.dff >= FD && s.dff <= FF && s.dff % FD == 0 && s.H == 1 && s.full_model == 1 && s.noise_on == 1 &&
          s.weights_mode == SMCT_WEIGHTS_GAUSSIAN && s.P <= FPMAX && s.P >= 1 && s.S <= 4096 && s.F_y <= 16 &&
          io.attn == nullptr;
 }

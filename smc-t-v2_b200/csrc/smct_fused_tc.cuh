@@ -100,16 +100,17 @@ __global__ void __launch_bounds__(FNT, 1) fused_tc_forward_kernel(const FusedArg
     sm.bz[i] = a.p.bz[i]; sm.b2[i] = a.p.b2[i];
     sm.ln1g[i] = a.p.ln1_g[i]; sm.ln1b[i] = a.p.ln1_b[i]; sm.ln2g[i] = a.p.ln2_g[i]; sm.ln2b[i] = a.p.ln2_b[i];
   }
-  for (int i = tid; i < FF; i += FNT) sm.b1[i] = a.p.b1[i];
+  const int nch = a.dff / FD;                     // FFN chunks of 64 hidden units (1..4)
+  for (int i = tid; i < a.dff; i += FNT) sm.b1[i] = a.p.b1[i];
   for (int i = tid; i < FD * Fy; i += FNT) sm.Wo[i] = a.p.Wo[i];
-  if (tid == 0) sm.hdr = *reinterpret_cast<const TcHeader*>(a.wtc + (size_t)(1 + 2 * (FF / FD)) * 2 * tc::B_PART_BYTES);
+  if (tid == 0) sm.hdr = *reinterpret_cast<const TcHeader*>(a.wtc + (size_t)(1 + 2 * nch) * 2 * tc::B_PART_BYTES);
   if (wid == 0) tc::tmem_alloc(&sm.tmem_slot, 512);
   if (tid == 0) {
     tc::mbar_init(&sm.mbar_z, 1); tc::mbar_init(&sm.mbar_r, 1);
     for (int c = 0; c < FF / FD; ++c) tc::mbar_init(&sm.mbar_h[c], 1);
     tc::fence_mbar_init();
   }
-  for (int c = 0; c < FF / FD; ++c)   // W1 stays in shared memory for all tiles and timesteps
+  for (int c = 0; c < nch; ++c)   // W1 stays in shared memory for all tiles and timesteps
     copy_block_async(sm.W1all[c], a.wtc + (size_t)(1 + 2 * c) * 2 * tc::B_PART_BYTES, 2 * tc::B_PART_BYTES);
   cp_async_commit();
   cp_async_wait_all();
@@ -397,8 +398,10 @@ __global__ void __launch_bounds__(FNT, 1) fused_tc_forward_kernel(const FusedArg
       ph_z ^= 1;
       tc::fence_after_sync();
       // Wz has been consumed: W2 chunk 1 travels into its buffer during the LN1 epilogue
-      copy_block_async(sm.Ws[0], a.wtc + (size_t)4 * 2 * tc::B_PART_BYTES, 2 * tc::B_PART_BYTES);
-      cp_async_commit();
+      if (nch > 1) {
+        copy_block_async(sm.Ws[0], a.wtc + (size_t)4 * 2 * tc::B_PART_BYTES, 2 * tc::B_PART_BYTES);
+        cp_async_commit();
+      }
       {  // ---- z = dense(z_) + noise ; LN1(z + x) ----
         tmem_ld16(tD_z + tlane + n0, val);
         const float zscale = sm.rs[er] * sm.hdr.inv_wz;
@@ -452,12 +455,12 @@ __global__ void __launch_bounds__(FNT, 1) fused_tc_forward_kernel(const FusedArg
       // ---- FFN: the four first GEMMs (o · W1 chunk, W1 resident) are issued at once into four TMEM ranges; the relu /
       //      split epilogue of chunk c then overlaps the tensor-core work of the later chunks and of the second GEMMs ----
       if (wid == 0 && tc::elect_one()) {
-        for (int c = 0; c < FF / FD; ++c) {
+        for (int c = 0; c < nch; ++c) {
           tc::mma_block_bf16x3(tD_h + FD * c, tc::smem_u32(sm.Ob), tc::smem_u32(sm.W1all[c]), tc::B_PART_BYTES, idesc, false);
           tc::commit(&sm.mbar_h[c]);
         }
       }
-      for (int c = 0; c < FF / FD; ++c) {
+      for (int c = 0; c < nch; ++c) {
         tc::mbar_wait(&sm.mbar_h[c], ph_h);
         tc::fence_after_sync();
         tmem_ld16(tD_h + FD * c + tlane + n0, val);
@@ -469,14 +472,14 @@ __global__ void __launch_bounds__(FNT, 1) fused_tc_forward_kernel(const FusedArg
           tc::mbar_wait(&sm.mbar_r, ph_r);
           ph_r ^= 1;
           tc::fence_after_sync();
-          if (c + 1 < FF / FD) {
+          if (c + 1 < nch) {
             copy_block_async(sm.Ws[(c + 1 + 1) & 1], a.wtc + (size_t)(2 + 2 * (c + 1)) * 2 * tc::B_PART_BYTES, 2 * tc::B_PART_BYTES);
             cp_async_commit();
           }
         }
 #pragma unroll
         for (int gq = 0; gq < 4; ++gq) tc::store_a4(sm.ZH, er, n0 + 4 * gq, &hv[4 * gq]);
-        if (c == 0 || c + 1 == FF / FD) cp_async_wait_all(); else cp_async_wait_1();   // W2 chunk c has landed (chunk c+1 may still travel)
+        if (c == 0 || c + 1 == nch) cp_async_wait_all(); else cp_async_wait_1();   // W2 chunk c has landed (chunk c+1 may still travel)
         tc::fence_async_smem();
         tc::fence_before_sync();
         __syncthreads();

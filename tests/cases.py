@@ -31,7 +31,7 @@ BIG_CASES = {
     "c4_b2_s16": dict(cfg=Config(B=2, P=1024, S=16, D=64, dff=256), sigma2=0.5),
 }
 
-# shapes served by the fused persistent kernel (d_model 64, dff 256, 1 head, full model, gaussian weights)
+# shapes served by the fused persistent kernel (d_model 64, dff 64..256, 1 head, full model, gaussian weights)
 FUSED_CASES = {
     "f_p70": dict(cfg=Config(B=2, P=70, S=20, D=64, dff=256), sigma2=0.5),
     "f_p1": dict(cfg=Config(B=3, P=1, S=5, D=64, dff=256), sigma2=0.5),
@@ -41,4 +41,8 @@ FUSED_CASES = {
     "f_multi_pyc": dict(cfg=Config(B=2, P=33, S=8, D=64, dff=256, noise_z_mode="pyc", F_y=2), sigma2=0.2, multi=True),
     "f_s1": dict(cfg=Config(B=2, P=16, S=1, D=64, dff=256), sigma2=0.5),
     "f_p300": dict(cfg=Config(B=3, P=300, S=24, D=64, dff=256), sigma2=0.5),
+    # dff = 64, 128, 192: one to three FFN chunks of 64 hidden units
+    "f_dff64": dict(cfg=Config(B=2, P=50, S=10, D=64, dff=64), sigma2=0.5),
+    "f_dff128": dict(cfg=Config(B=2, P=130, S=8, D=64, dff=128, F_x=2, F_y=2), sigma2=0.3),
+    "f_dff192": dict(cfg=Config(B=2, P=33, S=9, D=64, dff=192), sigma2=0.5),
 }
