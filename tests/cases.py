@@ -45,4 +45,6 @@ FUSED_CASES = {
     "f_dff64": dict(cfg=Config(B=2, P=50, S=10, D=64, dff=64), sigma2=0.5),
     "f_dff128": dict(cfg=Config(B=2, P=130, S=8, D=64, dff=128, F_x=2, F_y=2), sigma2=0.3),
     "f_dff192": dict(cfg=Config(B=2, P=33, S=9, D=64, dff=192), sigma2=0.5),
+    # a long trajectory: many old slots per particle group (shared-unit fast path, several column groups per warp)
+    "f_s136": dict(cfg=Config(B=1, P=48, S=136, D=64, dff=128), sigma2=0.5),
 }
