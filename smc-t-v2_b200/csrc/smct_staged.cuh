@@ -117,9 +117,37 @@ struct StepArgs {
 };
 
 // C[row][c] = bias[c] + sum_k A[row][k] * W[k][c]  for the PT-row tile; epilogue(row, c, value).
+// Every output accumulates bias + the products in the order k = 0..Kdim-1 (fmaf), whichever blocking is used, so the
+// two paths below give identical bits.  Blocked path (N % 4 == 0, 16-byte aligned W): a thread owns 2 rows x 4 columns,
+// one 128-bit weight load per k feeds 8 FMAs (the scalar path issues 5 loads per 4 FMAs and is LSU-bound).
 template <typename Epi>
 __device__ __forceinline__ void tile_gemm(const float* __restrict__ A, int lda, const float* __restrict__ W,
                                           const float* __restrict__ bias, int Kdim, int N, Epi epi) {
+  if ((N & 3) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0) {
+    constexpr int RH = PT / 2;   // rows rg and rg + RH
+    const int N4 = N >> 2;
+    for (int j = threadIdx.x; j < N4 * RH; j += NT) {
+      const int c = 4 * (j % N4), rg = j / N4;
+      float acc[2][4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { const float b0 = bias ? bias[c + e] : 0.f; acc[0][e] = b0; acc[1][e] = b0; }
+      const float* Ar = A + rg * lda;
+#pragma unroll 4
+      for (int k = 0; k < Kdim; ++k) {
+        const float4 w = __ldg(reinterpret_cast<const float4*>(W + (long long)k * N + c));
+        const float a0 = Ar[k], a1 = Ar[RH * lda + k];
+        acc[0][0] = fmaf(a0, w.x, acc[0][0]); acc[0][1] = fmaf(a0, w.y, acc[0][1]);
+        acc[0][2] = fmaf(a0, w.z, acc[0][2]); acc[0][3] = fmaf(a0, w.w, acc[0][3]);
+        acc[1][0] = fmaf(a1, w.x, acc[1][0]); acc[1][1] = fmaf(a1, w.y, acc[1][1]);
+        acc[1][2] = fmaf(a1, w.z, acc[1][2]); acc[1][3] = fmaf(a1, w.w, acc[1][3]);
+      }
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) epi(rg + i * RH, c + e, acc[i][e]);
+    }
+    return;
+  }
   for (int j = threadIdx.x; j < N * RG; j += NT) {
     const int c = j % N, rg = j / N;
     float acc[RPT];
