@@ -231,8 +231,31 @@ __global__ void __launch_bounds__(256) bwd_attn_fwd_kernel(const BwdArgs a) {
 // dense forward recompute + backward: persistent CTAs, one tile = 32 consecutive nodes of the flat node list
 // (a tile may span several (b,s); every row carries its own b*S+s, ancestor id and multiplicity)
 // ------------------------------------------------------------------------------------------
-// rep[(k,n)] += sum_rows A[row][k] * Bm[row][n]   (CTA-private replica: plain read-modify-write)
+// rep[(k,n)] += sum_rows A[row][k] * Bm[row][n]   (CTA-private replica: plain read-modify-write).  Every output sums
+// its PT products in row order; the blocked path (2 k x 4 n per thread: 6 shared loads per 8 FMAs instead of 2 per 1)
+// gives the same bits as the scalar one.
 __device__ __forceinline__ void tile_outer_accum(const float* A, int lda, const float* Bm, int ldb, int Kdim, int N, float* rep) {
+  if ((Kdim & 1) == 0 && (N & 3) == 0) {
+    const int N4 = N >> 2, K2 = Kdim >> 1;
+    for (int idx = threadIdx.x; idx < K2 * N4; idx += NT) {
+      const int k = 2 * (idx / N4), n = 4 * (idx % N4);
+      float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+#pragma unroll 4
+      for (int r = 0; r < PT; ++r) {
+        const float a0 = A[r * lda + k], a1 = A[r * lda + k + 1];
+        const float b0 = Bm[r * ldb + n], b1 = Bm[r * ldb + n + 1], b2 = Bm[r * ldb + n + 2], b3 = Bm[r * ldb + n + 3];
+        acc[0][0] = fmaf(a0, b0, acc[0][0]); acc[0][1] = fmaf(a0, b1, acc[0][1]);
+        acc[0][2] = fmaf(a0, b2, acc[0][2]); acc[0][3] = fmaf(a0, b3, acc[0][3]);
+        acc[1][0] = fmaf(a1, b0, acc[1][0]); acc[1][1] = fmaf(a1, b1, acc[1][1]);
+        acc[1][2] = fmaf(a1, b2, acc[1][2]); acc[1][3] = fmaf(a1, b3, acc[1][3]);
+      }
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) rep[(k + i) * N + n + e] += acc[i][e];
+    }
+    return;
+  }
   for (int idx = threadIdx.x; idx < Kdim * N; idx += NT) {
     const int k = idx / N, n = idx - k * N;
     float acc = 0.f;
