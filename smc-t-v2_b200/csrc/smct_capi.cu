@@ -58,6 +58,18 @@ struct Carver {
   }
 };
 
+// cudaFuncSetAttribute applies to the CURRENT device: the "already done" flag of a launch site is kept per device so
+// that a process driving several GPUs configures each of them (one flag word per site, bit = device ordinal).
+struct PerDeviceOnce {
+  std::atomic<unsigned long long> done{0};
+  bool need() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned long long bit = 1ull << (dev & 63);
+    return (done.fetch_or(bit) & bit) == 0;
+  }
+};
+
 int check_shape(const smct_shape* s) {
   if (!s) return fail(SMCT_ERR_INVALID, "shape is NULL");
   if (s->struct_bytes != (int32_t)sizeof(smct_shape))
@@ -85,12 +97,11 @@ size_t step_smem_bytes(int D, int dff, int full_model) {
 
 template <int KD>
 int launch_step_t(const smct::StepArgs& a, cudaStream_t st) {
-  static bool attr_set = false;
+  static PerDeviceOnce attr_once;
   const size_t smem = step_smem_bytes(a.D, a.dff, a.full_model);
   if (smem > 200 * 1024) return fail(SMCT_ERR_UNSUPPORTED, "step tile needs %zu B shared memory (D=%d dff=%d)", smem, a.D, a.dff);
-  if (!attr_set) {
+  if (attr_once.need()) {
     SMCT_CUDA(cudaFuncSetAttribute(smct::step_kernel<KD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
   }
   dim3 grid((a.P + smct::PT - 1) / smct::PT, a.B);
   smct::step_kernel<KD><<<grid, smct::NT, smem, st>>>(a);
@@ -114,11 +125,10 @@ int launch_rows(const smct::RowsArgs& a, cudaStream_t st) {
 }
 
 int launch_resample(const smct::ResampleArgs& a, cudaStream_t st) {
-  static bool attr_set = false;
+  static PerDeviceOnce attr_once;
   const size_t smem = (size_t)a.P * sizeof(double);
-  if (smem > 48 * 1024 && !attr_set) {
+  if (smem > 48 * 1024 && attr_once.need()) {
     SMCT_CUDA(cudaFuncSetAttribute(smct::resample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    attr_set = true;
   }
   smct::resample_kernel<<<a.B, 256, smem, st>>>(a);
   SMCT_LAUNCH_CHECK("resample_kernel");
@@ -163,12 +173,11 @@ size_t staged_forward_ws(const smct_shape& s) {
 
 template <int KD>
 int launch_seq_t(const smct::SeqArgs& g, cudaStream_t st) {
-  static bool attr_set = false;
+  static PerDeviceOnce attr_once;
   const size_t smem = std::max(step_smem_bytes(g.step.D, g.step.dff, g.step.full_model), (size_t)g.step.P * sizeof(double));
   if (smem > 200 * 1024) return fail(SMCT_ERR_UNSUPPORTED, "per-sequence forward needs %zu B shared memory", smem);
-  if (!attr_set) {
+  if (attr_once.need()) {
     SMCT_CUDA(cudaFuncSetAttribute(smct::seq_forward_kernel<KD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
   }
   smct::seq_forward_kernel<KD><<<g.step.B, smct::NT, smem, st>>>(g);
   SMCT_LAUNCH_CHECK("seq_forward_kernel");
@@ -369,13 +378,12 @@ int forward_fused(const smct_shape& s, const smct_params& pr, const smct_io& io,
   a.pred = io.pred; a.w = io.w; a.logw = io.logw; a.noise_q = io.noise_q; a.noise_z = io.noise_z;
   a.i_out = io.i_out; a.loss_sums = io.loss_sums;
   a.wtc = wtc;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.need()) {
     SMCT_CUDA(cudaFuncSetAttribute(smct::fused_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)sizeof(smct::FusedSmem)));
     SMCT_CUDA(cudaFuncSetAttribute(smct::fused_tc_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)sizeof(smct::FusedTcSmem) + 1024));
-    attr_set = true;
   }
   if (use_tc) {
     smct::fused_tc_forward_kernel<<<B, smct::FNT, sizeof(smct::FusedTcSmem) + 1024, st>>>(a);
@@ -454,10 +462,9 @@ int launch_backward_t(const smct::BwdArgs& a, cudaStream_t st) {
   SMCT_LAUNCH_CHECK("bwd_attn_fwd_kernel");
   const size_t smem_d = ((size_t)5 * smct::PT * (D + 1) + 2 * smct::PT * (dff + 1) + smct::PT + 7 * D + dff + D * a.Fy) * sizeof(float);
   if (smem_d > 200 * 1024) return fail(SMCT_ERR_UNSUPPORTED, "backward dense tile needs %zu B shared memory", smem_d);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.need()) {
     SMCT_CUDA(cudaFuncSetAttribute(smct::bwd_dense_kernel<KD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
   }
   const long long ntiles = (nrows + smct::PT - 1) / smct::PT;
   smct::bwd_dense_kernel<KD><<<(int)std::min<long long>(ntiles, a.nrep), smct::NT, smem_d, st>>>(a);
@@ -773,11 +780,10 @@ int smct_backward(const smct_shape* shape, const smct_params* params, const smct
   SMCT_LAUNCH_CHECK("anc_trace_kernel");
   {  // unique (slot, ancestor) nodes of the final genealogy: count, scan, fill
     const size_t smem_n = (size_t)2 * P * sizeof(int);
-    static bool node_attr = false;
-    if (!node_attr) {
+    static PerDeviceOnce node_once;
+    if (node_once.need()) {
       SMCT_CUDA(cudaFuncSetAttribute(smct::node_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 12288 * (int)sizeof(int)));
       SMCT_CUDA(cudaFuncSetAttribute(smct::node_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 12288 * (int)sizeof(int)));
-      node_attr = true;
     }
     smct::node_count_kernel<<<B * S, 256, smem_n, st>>>(P, anc, node_cnt);
     SMCT_LAUNCH_CHECK("node_count_kernel");
@@ -834,10 +840,9 @@ int smct_tc_selftest(const float* A, const float* W, float* D, void* scratch, vo
   smct::tc_weight_prep_kernel<<<1, 1024, 0, st>>>(W, nullptr, nullptr, nullptr, nullptr, nullptr, 0, (unsigned char*)scratch);
   SMCT_LAUNCH_CHECK("tc_weight_prep_kernel");
   const int smem = 2 * smct::tc::A_PART_BYTES + 2 * smct::tc::B_PART_BYTES + 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.need()) {
     SMCT_CUDA(cudaFuncSetAttribute(smct::tc_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
   }
   smct::tc_selftest_kernel<<<1, 128, smem, st>>>(A, (const unsigned char*)scratch, D);
   SMCT_LAUNCH_CHECK("tc_selftest_kernel");

@@ -357,10 +357,14 @@ __global__ void __launch_bounds__(FNT, 1) fused_tc_forward_kernel(const FusedArg
             const int d0 = 16 * c + 4 * k4;
             *reinterpret_cast<float4*>(&sm.Os[R0 * FLD + d0]) = make_float4(z0[4 * k4], z0[4 * k4 + 1], z0[4 * k4 + 2], z0[4 * k4 + 3]);
             *reinterpret_cast<float4*>(&sm.Os[R1 * FLD + d0]) = make_float4(z1[4 * k4], z1[4 * k4 + 1], z1[4 * k4 + 2], z1[4 * k4 + 3]);
-            const float zz0[4] = {z0[4 * k4] * zs0, z0[4 * k4 + 1] * zs0, z0[4 * k4 + 2] * zs0, z0[4 * k4 + 3] * zs0};
-            const float zz1[4] = {z1[4 * k4] * zs1, z1[4 * k4 + 1] * zs1, z1[4 * k4 + 2] * zs1, z1[4 * k4 + 3] * zs1};
-            tc::store_a4(sm.ZH, R0, d0, zz0);
-            tc::store_a4(sm.ZH, R1, d0, zz1);
+          }
+#pragma unroll
+          for (int k8 = 0; k8 < 2; ++k8) {
+            float zz0[8], zz1[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { zz0[e] = z0[8 * k8 + e] * zs0; zz1[e] = z1[8 * k8 + e] * zs1; }
+            tc::store_a8(sm.ZH, R0, 16 * c + 8 * k8, zz0);
+            tc::store_a8(sm.ZH, R1, 16 * c + 8 * k8, zz1);
           }
         }
       }
@@ -444,9 +448,11 @@ __global__ void __launch_bounds__(FNT, 1) fused_tc_forward_kernel(const FusedArg
             o[e] = val[4 * gq + e] * inv + (sm.ln1b[n + e] - mean * inv);
           }
           *reinterpret_cast<float4*>(&sm.Os[er * FLD + n]) = make_float4(o[0], o[1], o[2], o[3]);
-          const float os[4] = {o[0] * sm.hdr.s_o, o[1] * sm.hdr.s_o, o[2] * sm.hdr.s_o, o[3] * sm.hdr.s_o};
-          tc::store_a4(sm.Ob, er, n, os);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) val[4 * gq + e] = o[e] * sm.hdr.s_o;
         }
+        tc::store_a8(sm.Ob, er, n0, &val[0]);
+        tc::store_a8(sm.Ob, er, n0 + 8, &val[8]);
       }
       tc::fence_async_smem();
       tc::fence_before_sync();
@@ -478,7 +484,7 @@ __global__ void __launch_bounds__(FNT, 1) fused_tc_forward_kernel(const FusedArg
           }
         }
 #pragma unroll
-        for (int gq = 0; gq < 4; ++gq) tc::store_a4(sm.ZH, er, n0 + 4 * gq, &hv[4 * gq]);
+        for (int g8 = 0; g8 < 2; ++g8) tc::store_a8(sm.ZH, er, n0 + 8 * g8, &hv[8 * g8]);
         if (c == 0 || c + 1 == nch) cp_async_wait_all(); else cp_async_wait_1();   // W2 chunk c has landed (chunk c+1 may still travel)
         tc::fence_async_smem();
         tc::fence_before_sync();

@@ -179,6 +179,18 @@ __device__ __forceinline__ void store_a4(unsigned char* base, int r, int k0, con
   *reinterpret_cast<uint2*>(base + A_PART_BYTES + off) = m;
 }
 
+// write 8 consecutive k-values (k0 % 8 == 0: one 16-byte row of a core matrix) of row r into an A operand tile.  A warp
+// of 32 consecutive rows then covers 32 banks per 8 rows with its 16-byte stores (store_a4's 8-byte stores hit every
+// bank four times).
+__device__ __forceinline__ void store_a8(unsigned char* base, int r, int k0, const float x[8]) {
+  uint2 h0, m0, h1, m1;
+  split4(x, h0, m0);
+  split4(x + 4, h1, m1);
+  const uint32_t off = operand_offset(r, k0);
+  *reinterpret_cast<uint4*>(base + off) = make_uint4(h0.x, h0.y, h1.x, h1.y);
+  *reinterpret_cast<uint4*>(base + A_PART_BYTES + off) = make_uint4(m0.x, m0.y, m1.x, m1.y);
+}
+
 }  // namespace tc
 
 // ------------------------------------------------------------------------------------------
