@@ -60,9 +60,9 @@ struct FusedResampleScratch {  // used only between the tiles of two timesteps (
 struct FusedCommon {           // per-sequence bookkeeping shared by both fused kernels
   float lw[FPMAX];
   unsigned short Lq[FPMAX], pos[FPMAX];
-  float rowbuf[4][FD];       // xln, q_, k_, v_ of the current step
-  float stdtab[4][FD];       // exp(0.5 logvar) for k,q,v,z
-  float ivar[4][FD];         // exp(-logvar)
+  __align__(16) float rowbuf[4][FD];   // xln, q_, k_, v_ of the current step (16-byte aligned: read as float4)
+  __align__(16) float stdtab[4][FD];   // exp(0.5 logvar) for k,q,v,z
+  __align__(16) float ivar[4][FD];     // exp(-logvar)
   float red[64];
   double dred[2];
 };

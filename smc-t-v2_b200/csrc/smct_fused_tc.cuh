@@ -21,7 +21,7 @@ namespace smct {
 
 struct FusedTcSmem {
   FusedCommon c;
-  float bz[FD], b1[FF], b2[FD], ln1g[FD], ln1b[FD], ln2g[FD], ln2b[FD], Wo[FD * 16];
+  __align__(16) float bz[FD], b1[FF], b2[FD], ln1g[FD], ln1b[FD], ln2g[FD], ln2b[FD], Wo[FD * 16];   // read as float4
   float psum[2][4][FTILE];
   float rs[FTILE];                                    // per-row inverse power-of-two scale of the z_ operand
   TcHeader hdr;                                       // weight / activation scales (tc_weight_prep_kernel)
@@ -61,6 +61,12 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float v[16]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// four consecutive per-column constants (16-byte aligned shared arrays) with one 128-bit load
+__device__ __forceinline__ void ld4(const float* p, float v[4]) {
+  const float4 t = *reinterpret_cast<const float4*>(p);
+  v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
 }
 
 __global__ void __launch_bounds__(FNT, 1) fused_tc_forward_kernel(const FusedArgs a) {
@@ -174,14 +180,15 @@ __global__ void __launch_bounds__(FNT, 1) fused_tc_forward_kernel(const FusedArg
           const float kin[4] = {k_0.x, k_0.y, k_0.z, k_0.w};
           const float qin[4] = {q_0.x, q_0.y, q_0.z, q_0.w};
           const float vin[4] = {v_0.x, v_0.y, v_0.z, v_0.w};
-          float qo[4], nq[4];
+          float qo[4], nq[4], sdk[4], sdq[4], sdv[4], ivq[4];
+          ld4(&sm.c.stdtab[0][d0], sdk); ld4(&sm.c.stdtab[1][d0], sdq); ld4(&sm.c.stdtab[2][d0], sdv); ld4(&sm.c.ivar[1][d0], ivq);
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            ko[4 * i + e] = __fadd_rn(kin[e], __fmul_rn(sm.c.stdtab[0][d0 + e], ek[e]));
-            qo[e] = __fadd_rn(qin[e], __fmul_rn(sm.c.stdtab[1][d0 + e], eq[e]));
-            vo[4 * i + e] = __fadd_rn(vin[e], __fmul_rn(sm.c.stdtab[2][d0 + e], ev[e]));
+            ko[4 * i + e] = __fadd_rn(kin[e], __fmul_rn(sdk[e], ek[e]));
+            qo[e] = __fadd_rn(qin[e], __fmul_rn(sdq[e], eq[e]));
+            vo[4 * i + e] = __fadd_rn(vin[e], __fmul_rn(sdv[e], ev[e]));
             nq[e] = qo[e] - qin[e];
-            loss_q = act ? fmaf(nq[e] * nq[e], sm.c.ivar[1][d0 + e], loss_q) : loss_q;
+            loss_q = act ? fmaf(nq[e] * nq[e], ivq[e], loss_q) : loss_q;
           }
           // q tile for the MMA fragments: scaled by log2(e)/sqrt(d_k) (scores in the log2 domain) and the fp16 scale
           const float qs = sm.hdr.s_q;
@@ -415,14 +422,15 @@ __global__ void __launch_bounds__(FNT, 1) fused_tc_forward_kernel(const FusedArg
           const int n = n0 + 4 * gq;
           const float4 zold = *reinterpret_cast<const float4*>(&sm.Os[er * FLD + n]);
           const float z_[4] = {zold.x, zold.y, zold.z, zold.w};
-          float nzv[4];
+          float nzv[4], cbz[4], csd[4], civ[4], cx[4];
+          ld4(&sm.bz[n], cbz); ld4(&sm.c.stdtab[3][n], csd); ld4(&sm.c.ivar[3][n], civ); ld4(&sm.c.rowbuf[0][n], cx);
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const float zp = fmaf(val[4 * gq + e], zscale, sm.bz[n + e]);   // scale is a power of two: exact
-            const float z = __fadd_rn(zp, __fmul_rn(sm.c.stdtab[3][n + e], ezv[4 * gq + e]));
+            const float zp = fmaf(val[4 * gq + e], zscale, cbz[e]);   // scale is a power of two: exact
+            const float z = __fadd_rn(zp, __fmul_rn(csd[e], ezv[4 * gq + e]));
             nzv[e] = (a.noise_z_mode == SMCT_NOISE_Z_CHECKOUT) ? (z - z_[e]) : (z - zp);
-            loss_z = eact ? fmaf(nzv[e] * nzv[e], sm.c.ivar[3][n + e], loss_z) : loss_z;
-            val[4 * gq + e] = z + sm.c.rowbuf[0][n + e];
+            loss_z = eact ? fmaf(nzv[e] * nzv[e], civ[e], loss_z) : loss_z;
+            val[4 * gq + e] = z + cx[e];
             s1 += val[4 * gq + e];
           }
           if (eact && a.noise_z)
@@ -441,11 +449,12 @@ __global__ void __launch_bounds__(FNT, 1) fused_tc_forward_kernel(const FusedArg
 #pragma unroll
         for (int gq = 0; gq < 4; ++gq) {
           const int n = n0 + 4 * gq;
-          float o[4];
+          float o[4], cg[4], cb[4];
+          ld4(&sm.ln1g[n], cg); ld4(&sm.ln1b[n], cb);
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const float inv = rstd * sm.ln1g[n + e];
-            o[e] = val[4 * gq + e] * inv + (sm.ln1b[n + e] - mean * inv);
+            const float inv = rstd * cg[e];
+            o[e] = val[4 * gq + e] * inv + (cb[e] - mean * inv);
           }
           *reinterpret_cast<float4*>(&sm.Os[er * FLD + n]) = make_float4(o[0], o[1], o[2], o[3]);
 #pragma unroll
@@ -473,7 +482,12 @@ __global__ void __launch_bounds__(FNT, 1) fused_tc_forward_kernel(const FusedArg
         const float hscale = sm.hdr.inv_o * sm.hdr.inv_w1;
         float hv[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) hv[j] = fmaxf(fmaf(val[j], hscale, sm.b1[c * FD + n0 + j]), 0.f) * sm.hdr.s_h;
+        for (int j4 = 0; j4 < 4; ++j4) {
+          float cb1[4];
+          ld4(&sm.b1[c * FD + n0 + 4 * j4], cb1);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) hv[4 * j4 + e] = fmaxf(fmaf(val[4 * j4 + e], hscale, cb1[e]), 0.f) * sm.hdr.s_h;
+        }
         if (c > 0) {   // the previous second GEMM has read ZH and its W2 buffer: both may be refilled
           tc::mbar_wait(&sm.mbar_r, ph_r);
           ph_r ^= 1;
@@ -508,9 +522,11 @@ __global__ void __launch_bounds__(FNT, 1) fused_tc_forward_kernel(const FusedArg
           const int n = n0 + 4 * gq;
           const float4 o4 = *reinterpret_cast<const float4*>(&sm.Os[er * FLD + n]);
           const float o[4] = {o4.x, o4.y, o4.z, o4.w};
+          float cb2[4];
+          ld4(&sm.b2[n], cb2);
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            val[4 * gq + e] = fmaf(val[4 * gq + e], rscale, sm.b2[n + e]) + o[e];
+            val[4 * gq + e] = fmaf(val[4 * gq + e], rscale, cb2[e]) + o[e];
             s1 += val[4 * gq + e];
           }
         }
@@ -528,11 +544,12 @@ __global__ void __launch_bounds__(FNT, 1) fused_tc_forward_kernel(const FusedArg
 #pragma unroll
         for (int gq = 0; gq < 4; ++gq) {
           const int n = n0 + 4 * gq;
-          float r4[4];
+          float r4[4], cg[4], cb[4];
+          ld4(&sm.ln2g[n], cg); ld4(&sm.ln2b[n], cb);
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const float inv = rstd * sm.ln2g[n + e];
-            r4[e] = val[4 * gq + e] * inv + (sm.ln2b[n + e] - mean * inv);
+            const float inv = rstd * cg[e];
+            r4[e] = val[4 * gq + e] * inv + (cb[e] - mean * inv);
           }
           *reinterpret_cast<float4*>(&sm.Os[er * FLD + n]) = make_float4(r4[0], r4[1], r4[2], r4[3]);
           if (eact) __stcs(reinterpret_cast<float4*>(rrow + n), make_float4(r4[0], r4[1], r4[2], r4[3]));   // read again only by the final pass
