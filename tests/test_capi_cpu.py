@@ -92,3 +92,16 @@ def test_no_cpu_fallback():
         pytest.skip("GPU present")
     with pytest.raises(RuntimeError):
         F.fill_uniform(0, 0, 0, 1, 1)
+
+
+def test_binding_enums_match_the_header():
+    """The ctypes binding's name -> value tables must be the header's enums (SMCT_ALGO_*, SMCT_WEIGHTS_*, ...)."""
+    from smct_b200 import _lib
+    src = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    enums = {k: int(v) for k, v in re.findall(r"\b(SMCT_[A-Z_0-9]+)\s*=\s*(-?\d+)", src)}
+    for table, prefix in ((_lib.ALGO, "SMCT_ALGO_"), (_lib.WEIGHTS, "SMCT_WEIGHTS_"), (_lib.NOISE_Z, "SMCT_NOISE_Z_"),
+                          (_lib.INPUT, "SMCT_INPUT_"), (_lib.LOSS, "SMCT_LOSS_")):
+        declared = {k[len(prefix):].lower(): v for k, v in enums.items() if k.startswith(prefix)}
+        assert table == declared, (prefix, table, declared)
+    assert (enums["SMCT_OK"], enums["SMCT_ERR_INVALID"], enums["SMCT_ERR_CUDA"], enums["SMCT_ERR_WORKSPACE"],
+            enums["SMCT_ERR_UNSUPPORTED"]) == (_lib.OK, _lib.ERR_INVALID, _lib.ERR_CUDA, _lib.ERR_WORKSPACE, _lib.ERR_UNSUPPORTED)

@@ -134,6 +134,24 @@ def test_eager_torch_restatement_agrees_with_numpy_oracle(name):
     assert np.isclose(E.loss_pyc(cfg, tp, out, torch.from_numpy(y)), O.smc_loss(cfg, p, ora, y, "pyc")[0], rtol=1e-4)
 
 
+def test_eager_torch_restatement_classification_variant():
+    """The nlp checkout's variant (Embedding input, softmax(pred)[y] weights passed as logits, sparse cross-entropy): the
+    torch restatement (gradient oracle of the backward tests) against the numpy oracle, forward and loss."""
+    torch = pytest.importorskip("torch")
+    from oracle import ref_eager_torch as E
+    c = CASES["classification"]
+    cfg = c["cfg"]
+    p, x_in, y, eps, u = util_cpu.make_case(cfg, seed=4, sigma2=c["sigma2"])
+    ora = O.forward(cfg, p, x_in, y, eps, u)
+    tp = {k: torch.from_numpy(np.asarray(v, np.float32)) for k, v in p.items()}
+    out = E.forward(cfg, tp, torch.from_numpy(x_in), torch.from_numpy(y), torch.from_numpy(eps), i_forced=torch.from_numpy(ora["i_t"]))
+    for k in ("pred", "pred_resampl", "K", "V", "R", "w", "noise_q", "noise_z", "noise_K_resampled"):
+        assert np.allclose(out[k].numpy(), ora[k], rtol=2e-4, atol=2e-5), k
+    loss, grads = E.loss_and_grads(cfg, p, x_in, y, eps, ora["i_t"], variant="checkout")
+    assert np.isclose(loss, O.smc_loss(cfg, p, ora, y, "checkout")[0], rtol=1e-5)
+    assert all(np.isfinite(g).all() for g in grads.values()) and np.abs(grads["W_in"]).max() > 0
+
+
 # ------------------------------------------------------------------------------------------------
 # the oracle against the outputs of the reference's OWN Python sources (run over oracle/tf_shim.py)
 # ------------------------------------------------------------------------------------------------
