@@ -48,3 +48,16 @@ def test_fused_forward_fuzz(B, P, S, dff, F, window, seed):
     for algo in ("fused", "fused_ffma"):
         dev = util.run_device(cfg, p, x_in, y, eps, u, want=want, algo=algo)
         util.compare_forward(cfg, p, dev, ora, y)
+
+
+@settings(max_examples=40, deadline=None, derandomize=True, suppress_health_check=list(HealthCheck))
+@given(B=st.integers(1, 3), P=st.integers(1, 24), S=st.integers(1, 8), D=st.sampled_from([4, 8, 16, 40]),
+       dff=st.sampled_from([4, 8, 20]), F=st.integers(1, 3), window=st.one_of(st.none(), st.integers(1, 4)),
+       stop=st.one_of(st.none(), st.integers(0, 8)), variant=st.sampled_from(["pyc", "checkout"]), seed=st.integers(0, 999))
+def test_backward_fuzz(B, P, S, D, dff, F, window, stop, variant, seed):
+    """smct_backward (node de-duplication, multiplicity weights) against fp64 torch autograd on random small shapes."""
+    from tests.test_gpu_backward import _compare, _run
+    cfg = O.Config(B=B, P=P, S=S, D=D, dff=dff, F_x=F, F_y=F, attn_window=window,
+                   len_resampling=None if stop is None else min(stop, S), noise_z_mode="pyc")
+    got, ref, _ = _run(cfg, variant, seed=seed)
+    _compare("fuzz", got, ref)
