@@ -11,6 +11,7 @@ from smct_b200.train.optimizers import Adam, CustomSchedule
 ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=148); ap.add_argument("--P", type=int, default=1024)
 ap.add_argument("--S", type=int, default=128); ap.add_argument("--steps", type=int, default=2); ap.add_argument("--warmup", type=int, default=1)
+ap.add_argument("--chunks", type=int, default=1, help="resident chunks of --batch sequences per optimiser step (gradients accumulated; 28 chunks of 148 = the C5 batch of 4096+ sequences per GPU)")
 a = ap.parse_args()
 world, rank, local = int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)
@@ -21,19 +22,26 @@ if world > 1:
 dev = torch.device("cuda", local)
 B, P, S, D, dff, Fdim = a.batch, a.P, a.S, 64, 256, 1
 params = {k: torch.as_tensor(v, device=dev) for k, v in utils.init_parameters(D, dff, Fdim, Fdim, sigma2=0.5).items()}
-x, y = utils.synthetic_ar1(B, S, Fdim, 0.9, 0.3, seed=1234 + rank)
-tx, ty = torch.as_tensor(x, device=dev), torch.as_tensor(y, device=dev)
-shape = F.make_shape(B, P, S, D, dff=dff, F_x=Fdim, F_y=Fdim, noise_z_mode="pyc", algo="auto", b_global0=rank * B)
+NC = a.chunks
+x, y = utils.synthetic_ar1(B * NC, S, Fdim, 0.9, 0.3, seed=1234 + rank)
+tx_all, ty_all = torch.as_tensor(x, device=dev), torch.as_tensor(y, device=dev)
+shapes = [F.make_shape(B, P, S, D, dff=dff, F_x=Fdim, F_y=Fdim, noise_z_mode="pyc", algo="auto", b_global0=(rank * NC + c) * B)
+          for c in range(NC)]
+shape, tx, ty = shapes[0], tx_all[:B], ty_all[:B]
 opt = Adam(CustomSchedule(D), beta_1=0.9, beta_2=0.98, epsilon=1e-9)
 names = sorted(n for n in params)
-inv_n = 1.0 / (float(B) * world * P * S)
+inv_n = 1.0 / (float(B) * NC * world * P * S)
 out = None
 
 def step(i):
     global out
-    out = F.forward(shape, params, tx, ty, seed=100 + i, want=("i_out", "loss_sums"), out=out)
-    grads = F.backward(shape, params, tx, ty, out, seed=100 + i, inv_n=inv_n)
-    flat = torch.cat([grads[n].reshape(-1) for n in names] + [out["loss_sums"].float()])
+    grads, sums = None, torch.zeros(8, dtype=torch.float64, device=dev)
+    for c in range(NC):   # chunks of the batch: forward + backward per chunk, gradients accumulated with the global 1/n
+        xc, yc = tx_all[c * B:(c + 1) * B], ty_all[c * B:(c + 1) * B]
+        out = F.forward(shapes[c], params, xc, yc, seed=100 + i, want=("i_out", "loss_sums"), out=out)
+        grads = F.backward(shapes[c], params, xc, yc, out, seed=100 + i, inv_n=inv_n, grads=grads)
+        sums += out["loss_sums"]
+    flat = torch.cat([grads[n].reshape(-1) for n in names] + [sums.float()])
     if dist is not None:
         dist.all_reduce(flat)
     o = 0
@@ -66,11 +74,11 @@ out2 = F.forward(shape, params, tx, ty, seed=1, want=("i_out", "loss_sums"), out
 torch.cuda.synchronize(); e0.record(); F.forward(shape, params, tx, ty, seed=2, want=("i_out", "loss_sums"), out=out); e1.record(); torch.cuda.synchronize()
 fwd_ms = e0.elapsed_time(e1)
 if rank == 0:
-    n = float(B) * world * P * S
+    n = float(B) * NC * world * P * S
     tot = sums.double().cpu().numpy()
     loss = (0.5 * tot[:4].sum() + tot[4]) / n   # sigma_obs = 0.5
     print(json.dumps({"what": "SMC-T training step (fwd + bwd + NCCL grad all-reduce + Adam)", "n_gpus": world,
-                      "per_gpu_batch": B, "P": P, "S": S, "d_model": D, "dff": dff, "ms_per_step": float(t.item()),
+                      "per_gpu_batch": B * NC, "chunks_per_step": NC, "P": P, "S": S, "d_model": D, "dff": dff, "ms_per_step": float(t.item()),
                       "forward_ms": fwd_ms, "particle_steps_per_s": n / (float(t.item()) * 1e-3), "loss": float(loss),
                       "grad_elems_allreduced": int(sum(params[k].numel() for k in names))}))
 if dist is not None:
