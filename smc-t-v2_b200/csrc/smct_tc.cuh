@@ -11,7 +11,7 @@
 // (A bf16 split needs no scaling but keeps only 16 bits: measured error 1.5e-5 of the tensor scale.)
 //
 // Operand layout (K-major, no swizzle; cute "INTERLEAVE" canonical layout ((8,n),2):((1,SBO),LBO) in 16-byte
-// units): a tile of R rows x 64 k-values of bf16 is stored as 8x8 "core matrices" of 128 bytes
+// units): a tile of R rows x 64 k-values of fp16 is stored as 8x8 "core matrices" of 128 bytes
 // (8 rows x 16 bytes); element (r,k) lives at byte
 //     (r/8)*1024 + (k/8)*128 + (r%8)*16 + (k%8)*2        -> LBO = 128 B (next core along K), SBO = 1024 B.
 // One tcgen05.mma consumes K = 16 (two cores along K): K-step j starts at byte offset 256*j.
@@ -25,8 +25,8 @@ namespace tc {
 
 constexpr uint32_t LBO_BYTES = 128;
 constexpr uint32_t SBO_BYTES = 1024;
-constexpr uint32_t A_PART_BYTES = 128 * 64 * 2;   // one bf16 part (h or m) of a 128x64 A tile: 16 KB
-constexpr uint32_t B_PART_BYTES = 64 * 64 * 2;    // one bf16 part of a 64(N)x64(K) B block: 8 KB
+constexpr uint32_t A_PART_BYTES = 128 * 64 * 2;   // one fp16 part (h or m) of a 128x64 A tile: 16 KB
+constexpr uint32_t B_PART_BYTES = 64 * 64 * 2;    // one fp16 part of a 64(N)x64(K) B block: 8 KB
 
 __device__ __forceinline__ uint32_t operand_offset(int r, int k) {
   return (uint32_t)((r >> 3) * (int)SBO_BYTES + (k >> 3) * (int)LBO_BYTES + (r & 7) * 16 + (k & 7) * 2);
@@ -66,11 +66,11 @@ __device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t desc_a, uint64
       : "memory");
 }
 
-// D[128 x N] (+)= A[128 x 64] * B[N x 64]^T with the three-term bf16 split.  One thread issues.
+// D[128 x N] (+)= A[128 x 64] * B[N x 64]^T with the three-term fp16 split.  One thread issues.
 // a_base / b_base: shared addresses of the h part; the m part follows at +A_PART_BYTES / +b_part_bytes.
 // The start-address field of a descriptor is (address >> 4) in bits [0,14): with < 256 KB of shared memory an offset
 // can simply be added to a base descriptor (no carry into the other fields), which keeps the single issuing thread short.
-__device__ __forceinline__ void mma_block_bf16x3(uint32_t tmem_d, uint32_t a_base, uint32_t b_base, uint32_t b_part_bytes,
+__device__ __forceinline__ void mma_block_f16x3(uint32_t tmem_d, uint32_t a_base, uint32_t b_base, uint32_t b_part_bytes,
                                                  uint32_t idesc, bool accumulate) {
   const uint64_t da0 = make_desc(a_base), db0 = make_desc(b_base);
   const uint32_t a_off[3] = {0u, A_PART_BYTES, 0u};
@@ -330,7 +330,7 @@ __global__ void __launch_bounds__(128) tc_selftest_kernel(const float* A, const 
   tc::fence_after_sync();
   const uint32_t tmem = tmem_slot;
   if (tid == 0) {
-    tc::mma_block_bf16x3(tmem, tc::smem_u32(As), tc::smem_u32(Bs), tc::B_PART_BYTES, tc::make_idesc(128, 64), false);
+    tc::mma_block_f16x3(tmem, tc::smem_u32(As), tc::smem_u32(Bs), tc::B_PART_BYTES, tc::make_idesc(128, 64), false);
     tc::commit(&mbar);
   }
   tc::mbar_wait(&mbar, 0);
