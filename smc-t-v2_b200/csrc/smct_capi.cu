@@ -92,7 +92,7 @@ int check_shape(const smct_shape* s) {
 
 size_t step_smem_bytes(int D, int dff, int full_model) {
   const size_t Dp = D + 1, Fp = dff + 1;
-  return (2 * smct::PT * Dp + (full_model ? smct::PT * Fp : 0) + smct::NW * 3 * (size_t)D + 2 * smct::NW) * sizeof(float);
+  return (2 * smct::PT * Dp + (full_model ? smct::PT * Fp : 0) + smct::NW_MAX * 3 * (size_t)D + 2 * smct::NW_MAX) * sizeof(float);
 }
 
 template <int KD>
@@ -104,7 +104,7 @@ int launch_step_t(const smct::StepArgs& a, cudaStream_t st) {
     SMCT_CUDA(cudaFuncSetAttribute(smct::step_kernel<KD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   }
   dim3 grid((a.P + smct::PT - 1) / smct::PT, a.B);
-  smct::step_kernel<KD><<<grid, smct::NT, smem, st>>>(a);
+  smct::step_kernel<KD><<<grid, KD <= 2 ? smct::NT_WIDE : smct::NT, smem, st>>>(a);
   SMCT_LAUNCH_CHECK("step_kernel");
   return SMCT_OK;
 }
@@ -179,7 +179,7 @@ int launch_seq_t(const smct::SeqArgs& g, cudaStream_t st) {
   if (attr_once.need()) {
     SMCT_CUDA(cudaFuncSetAttribute(smct::seq_forward_kernel<KD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   }
-  smct::seq_forward_kernel<KD><<<g.step.B, smct::NT, smem, st>>>(g);
+  smct::seq_forward_kernel<KD><<<g.step.B, KD <= 2 ? smct::NT_WIDE : smct::NT, smem, st>>>(g);
   SMCT_LAUNCH_CHECK("seq_forward_kernel");
   return SMCT_OK;
 }

@@ -14,8 +14,11 @@
 namespace smct {
 
 constexpr int PT = 32;          // particles per CTA tile in step_kernel
-constexpr int NT = 256;         // threads per CTA in step_kernel
+constexpr int NT = 256;         // threads per CTA of the tile kernels (backward dense, step_kernel for d_model > 64)
 constexpr int NW = NT / 32;
+constexpr int NT_WIDE = 512;    // step_kernel / seq_forward_kernel for d_model <= 64: twice the warps for the per-particle
+                                // phases (they are bound by the latency of one warp walking a particle's history)
+constexpr int NW_MAX = NT_WIDE / 32;
 constexpr int RPT = 4;          // rows per thread in the tile GEMM
 constexpr int RG = PT / RPT;
 
@@ -126,7 +129,7 @@ __device__ __forceinline__ void tile_gemm(const float* __restrict__ A, int lda, 
   if ((N & 3) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0) {
     constexpr int RH = PT / 2;   // rows rg and rg + RH
     const int N4 = N >> 2;
-    for (int j = threadIdx.x; j < N4 * RH; j += NT) {
+    for (int j = threadIdx.x; j < N4 * RH; j += (int)blockDim.x) {
       const int c = 4 * (j % N4), rg = j / N4;
       float acc[2][4];
 #pragma unroll
@@ -148,7 +151,7 @@ __device__ __forceinline__ void tile_gemm(const float* __restrict__ A, int lda, 
     }
     return;
   }
-  for (int j = threadIdx.x; j < N * RG; j += NT) {
+  for (int j = threadIdx.x; j < N * RG; j += (int)blockDim.x) {
     const int c = j % N, rg = j / N;
     float acc[RPT];
     const float b0 = bias ? bias[c] : 0.f;
@@ -170,11 +173,12 @@ __device__ __forceinline__ void tile_gemm(const float* __restrict__ A, int lda, 
 template <int KD>
 __device__ __forceinline__ void step_tile(const StepArgs& a, const int b, const int p0, float* sm) {
   const int D = a.D, Dp = D + 1, dff = a.dff, Fp = dff + 1, S = a.S, t = a.t;
+  const int nt = (int)blockDim.x, nw = nt >> 5;   // 256 or 512 threads
   float* Zs = sm;
   float* Os = Zs + PT * Dp;
   float* Hs = Os + PT * Dp;
   float* scr = Hs + (a.full_model ? PT * Fp : 0);
-  float* red = scr + NW * 3 * D;  // 2*NW floats for loss partials
+  float* red = scr + nw * 3 * D;  // 2*nw floats for loss partials
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int np = min(PT, a.P - p0);
   const int Dh = D / a.H;
@@ -184,11 +188,11 @@ __device__ __forceinline__ void step_tile(const StepArgs& a, const int b, const 
   float loss_q = 0.f, loss_z = 0.f;
 
   // zero the tile so that rows >= np are defined for the GEMM phases
-  for (int i = tid; i < 2 * PT * Dp; i += NT) sm[i] = 0.f;
+  for (int i = tid; i < 2 * PT * Dp; i += nt) sm[i] = 0.f;
   __syncthreads();
 
   // ---------------- phase A: noise, slot-t store, attention (one warp per particle) ----------------
-  for (int pl = wid; pl < np; pl += NW) {
+  for (int pl = wid; pl < np; pl += nw) {
     const int p = p0 + pl;
     const long long bp = (long long)b * a.P + p;
     const long long row = (long long)b * a.row_sb + (long long)p * a.row_sp;
@@ -340,12 +344,12 @@ __device__ __forceinline__ void step_tile(const StepArgs& a, const int b, const 
   }
   if (a.loss_sums && a.noise_on) {
     const float sq = warp_sum(loss_q), sz = warp_sum(loss_z);
-    if (lane == 0) { red[wid] = sq; red[NW + wid] = sz; }
+    if (lane == 0) { red[wid] = sq; red[nw + wid] = sz; }
   }
   __syncthreads();
   if (a.loss_sums && a.noise_on && tid == 0) {
     double sq = 0.0, sz = 0.0;
-    for (int i = 0; i < NW; ++i) { sq += (double)red[i]; sz += (double)red[NW + i]; }
+    for (int i = 0; i < nw; ++i) { sq += (double)red[i]; sz += (double)red[nw + i]; }
     atomicAdd(a.loss_sums + 1, sq);
     atomicAdd(a.loss_sums + 3, sz);
   }
@@ -353,7 +357,7 @@ __device__ __forceinline__ void step_tile(const StepArgs& a, const int b, const 
 
   if (a.full_model) {
     // ---------------- phase C: o = LN1(z + x) (warp per row) ----------------
-    for (int pl = wid; pl < np; pl += NW) {
+    for (int pl = wid; pl < np; pl += nw) {
       const long long row = (long long)b * a.row_sb + (long long)(p0 + pl) * a.row_sp;
       float v[KD], s1 = 0.f;
 #pragma unroll
@@ -388,7 +392,7 @@ __device__ __forceinline__ void step_tile(const StepArgs& a, const int b, const 
     __syncthreads();
   }
   // ---------------- phase E: r = LN2(.), R store, output layer, log-weight (warp per row) ----------------
-  for (int pl = wid; pl < np; pl += NW) {
+  for (int pl = wid; pl < np; pl += nw) {
     const int p = p0 + pl;
     const long long bp = (long long)b * a.P + p;
     float r[KD];
@@ -464,7 +468,7 @@ __device__ __forceinline__ void step_tile(const StepArgs& a, const int b, const 
 }
 
 template <int KD>
-__global__ void __launch_bounds__(NT) step_kernel(const StepArgs a) {
+__global__ void __launch_bounds__(KD <= 2 ? NT_WIDE : NT) step_kernel(const StepArgs a) {
   extern __shared__ float sm[];
   step_tile<KD>(a, blockIdx.y, blockIdx.x * PT, sm);
 }
@@ -607,7 +611,7 @@ struct SeqArgs {
 };
 
 template <int KD>
-__global__ void __launch_bounds__(NT) seq_forward_kernel(const SeqArgs g) {
+__global__ void __launch_bounds__(KD <= 2 ? NT_WIDE : NT) seq_forward_kernel(const SeqArgs g) {
   extern __shared__ float sm[];
   __shared__ float scratch[32];
   __shared__ double total_s;
@@ -664,7 +668,7 @@ __global__ void __launch_bounds__(NT) seq_forward_kernel(const SeqArgs g) {
         for (int z = 0; z < 3; ++z) {
           const float* src = (z == 0 ? Kc : (z == 1 ? Vc : Rc)) + (size_t)b * P * stride;
           float* dst = (z == 0 ? Ka : (z == 1 ? Va : Ra)) + (size_t)b * P * stride;
-          for (long long i = tid; i < n; i += NT) {
+          for (long long i = tid; i < n; i += (long long)blockDim.x) {
             const int m = (int)(i / rowlen);
             const long long off = i - (long long)m * rowlen;
             dst[(long long)m * stride + off] = src[(long long)idx[m] * stride + off];
