@@ -135,10 +135,14 @@ int launch_resample(const smct::ResampleArgs& a, cudaStream_t st) {
   return SMCT_OK;
 }
 
-int launch_gather(const smct::GatherArgs& a, int ntensors, cudaStream_t st) {
+int launch_gather(const smct::GatherArgs& a_in, int ntensors, cudaStream_t st) {
+  smct::GatherArgs a = a_in;
   const long long per = ((a.row_elems & 3) == 0 && (a.n_elems & 3) == 0) ? a.n_elems / 4 : a.n_elems;
-  int gy = (int)std::max<long long>(1, std::min<long long>(64, (per + 256 * 8 - 1) / (256 * 8)));
-  dim3 grid((unsigned)((long long)a.B * a.P), gy, ntensors);
+  // short rows (the reference's small shapes): several particle rows per CTA, so that a CTA has ~1024 copy units
+  a.ppc = (int)std::max<long long>(1, std::min<long long>(64, 1024 / std::max<long long>(per, 1)));
+  const long long nbp = (long long)a.B * a.P;
+  int gy = (int)std::max<long long>(1, std::min<long long>(64, (per * a.ppc + 256 * 8 - 1) / (256 * 8)));
+  dim3 grid((unsigned)((nbp + a.ppc - 1) / a.ppc), gy, ntensors);
   smct::gather_kernel<<<grid, 256, 0, st>>>(a);
   SMCT_LAUNCH_CHECK("gather_kernel");
   return SMCT_OK;

@@ -561,6 +561,7 @@ __global__ void __launch_bounds__(256) resample_kernel(const ResampleArgs a) {
 // ------------------------------------------------------------------------------------------
 struct GatherArgs {
   int B, P;
+  int ppc;                  // particle rows per CTA (short rows: several rows share a CTA instead of one tiny CTA each)
   long long row_elems, n_elems;
   const float* src[3];
   float* dst[3];
@@ -568,24 +569,35 @@ struct GatherArgs {
 };
 
 __global__ void __launch_bounds__(256) gather_kernel(const GatherArgs a) {
-  const long long bp = blockIdx.x;
-  const int b = (int)(bp / a.P);
   const int z = blockIdx.z;
   const float* sbase = z == 0 ? a.src[0] : (z == 1 ? a.src[1] : a.src[2]);
   float* dbase = z == 0 ? a.dst[0] : (z == 1 ? a.dst[1] : a.dst[2]);
-  const float* __restrict__ src = sbase + ((long long)b * a.P + a.idx[bp]) * a.row_elems;
-  float* __restrict__ dst = dbase + bp * a.row_elems;
   const long long n = a.n_elems;
   const bool vec = ((a.row_elems & 3) == 0) && ((n & 3) == 0) && ((((uintptr_t)sbase) | ((uintptr_t)dbase)) & 15) == 0;
-  if (vec) {
-    const float4* s4 = (const float4*)src;
-    float4* d4 = (float4*)dst;
-    const long long n4 = n >> 2;
-    for (long long i = (long long)blockIdx.y * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.y * blockDim.x)
-      d4[i] = s4[i];
-  } else {
-    for (long long i = (long long)blockIdx.y * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.y * blockDim.x)
-      dst[i] = src[i];
+  const long long nbp = (long long)a.B * a.P;
+  const long long bp0 = (long long)blockIdx.x * a.ppc;
+  const int rows = (int)min((long long)a.ppc, nbp - bp0);
+  const long long per = vec ? (n >> 2) : n;                       // copy units per row
+  if (a.ppc == 1) {   // long rows: one row per CTA (and grid.y slices of it), no per-unit index arithmetic
+    const int b = (int)(bp0 / a.P);
+    const float* __restrict__ src = sbase + ((long long)b * a.P + a.idx[bp0]) * a.row_elems;
+    float* __restrict__ dst = dbase + bp0 * a.row_elems;
+    if (vec) {
+      for (long long i = (long long)blockIdx.y * blockDim.x + threadIdx.x; i < per; i += (long long)gridDim.y * blockDim.x)
+        reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(src)[i];
+    } else {
+      for (long long i = (long long)blockIdx.y * blockDim.x + threadIdx.x; i < per; i += (long long)gridDim.y * blockDim.x)
+        dst[i] = src[i];
+    }
+    return;
+  }
+  const long long total = per * rows;
+  for (long long i = (long long)blockIdx.y * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.y * blockDim.x) {
+    const long long bp = bp0 + i / per, e = i % per;
+    const int b = (int)(bp / a.P);
+    const long long so = ((long long)b * a.P + a.idx[bp]) * a.row_elems, dofs = bp * a.row_elems;
+    if (vec) reinterpret_cast<float4*>(dbase + dofs)[e] = reinterpret_cast<const float4*>(sbase + so)[e];
+    else dbase[dofs + e] = sbase[so + e];
   }
 }
 
