@@ -1,4 +1,4 @@
-"""Host restatement of the device counter-based RNG (Philox4x32-10 + Box-Muller).
+"""Host restatement of the device counter-based RNG (Philox4x32-7 + Box-Muller).
 
 *** TEST INFRASTRUCTURE — NOT PRODUCT CODE. ***  (see oracle/smct_oracle.py header)
 
@@ -27,13 +27,21 @@ W1 = 0xBB67AE85
 MASK = np.uint64(0xFFFFFFFF)
 
 
+ROUNDS = 7   # = SMCT_PHILOX_ROUNDS (smc-t-v2_b200/csrc/smct_common.cuh): "Philox4x32-7", the smallest Crush-resistant variant
+
+
 def philox4x32_10(c0, c1, c2, c3, k0, k1):
-    """Vectorised Philox4x32-10 (Salmon et al., SC'11). All inputs uint32 arrays/scalars (broadcast)."""
+    """Philox4x32-10: the round function is pinned by the Random123 known-answer vectors (tests/test_oracle_cpu.py)."""
+    return philox4x32(c0, c1, c2, c3, k0, k1, rounds=10)
+
+
+def philox4x32(c0, c1, c2, c3, k0, k1, rounds=ROUNDS):
+    """Vectorised Philox4x32-R (Salmon et al., SC'11). All inputs uint32 arrays/scalars (broadcast)."""
     c0, c1, c2, c3 = (np.asarray(c, np.uint64) & MASK for c in (c0, c1, c2, c3))
     c0, c1, c2, c3 = np.broadcast_arrays(c0, c1, c2, c3)
     k0 = int(k0) & 0xFFFFFFFF
     k1 = int(k1) & 0xFFFFFFFF
-    for r in range(10):
+    for r in range(rounds):
         p0 = M0 * c0
         p1 = M1 * c2
         hi0, lo0 = p0 >> np.uint64(32), p0 & MASK
@@ -62,7 +70,7 @@ def normals(seed, stream, t, b0, B, P, D):
     GD = (D + 3) // 4
     bp = (np.arange(b0, b0 + B, dtype=np.uint64)[:, None] * np.uint64(P) + np.arange(P, dtype=np.uint64)[None, :])
     grp = bp[:, :, None] * np.uint64(GD) + np.arange(GD, dtype=np.uint64)[None, None, :]
-    x0, x1, x2, x3 = philox4x32_10(grp & MASK, grp >> np.uint64(32), np.uint64(stream), np.uint64(t),
+    x0, x1, x2, x3 = philox4x32(grp & MASK, grp >> np.uint64(32), np.uint64(stream), np.uint64(t),
                                    seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
     n0, n1 = box_muller(x0, x1)
     n2, n3 = box_muller(x2, x3)
@@ -72,7 +80,7 @@ def normals(seed, stream, t, b0, B, P, D):
 
 def uniforms(seed, t, b0, B, P):
     grp = (np.arange(b0, b0 + B, dtype=np.uint64)[:, None] * np.uint64(P) + np.arange(P, dtype=np.uint64)[None, :])
-    x0, x1, _, _ = philox4x32_10(grp & MASK, grp >> np.uint64(32), np.uint64(4), np.uint64(t),
+    x0, x1, _, _ = philox4x32(grp & MASK, grp >> np.uint64(32), np.uint64(4), np.uint64(t),
                                  seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
     hi = (x0 >> np.uint32(5)).astype(np.float64)
     lo = (x1 >> np.uint32(6)).astype(np.float64)

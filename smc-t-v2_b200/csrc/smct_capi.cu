@@ -15,6 +15,7 @@
 #include "smct_fused.cuh"
 #include "smct_tc.cuh"
 #include "smct_fused_tc.cuh"
+#include "smct_fused2.cuh"
 #include "smct_backward.cuh"
 
 namespace {
@@ -329,7 +330,8 @@ int forward_staged(const smct_shape& s, const smct_params& pr, const smct_io& io
 //                -> materialize_kernel -> final_kernel
 // ------------------------------------------------------------------------------------------
 int forward_fused(const smct_shape& s, const smct_params& pr, const smct_io& io, void* ws, size_t ws_bytes,
-                  cudaStream_t st, bool use_tc) {
+                  cudaStream_t st, int algo) {
+  const bool use_tc = algo != SMCT_ALGO_FUSED_FFMA;
   if (ws_bytes < smct::fused_forward_ws(s)) return fail(SMCT_ERR_WORKSPACE, "workspace %zu < required %zu", ws_bytes, smct::fused_forward_ws(s));
   const int B = s.B, P = s.P, S = s.S, D = s.D;
   const int Sa = (S + 7) / 8 * 8;
@@ -351,11 +353,11 @@ int forward_fused(const smct_shape& s, const smct_params& pr, const smct_io& io,
   unsigned short* A1 = c.take<unsigned short>((size_t)B * P * Sa);
   unsigned short* pos = c.take<unsigned short>((size_t)B * P);
   int* aflag = c.take<int>((size_t)B);
-  unsigned char* wtc = c.take<unsigned char>((size_t)(1 + 2 * (smct::FF / smct::FD)) * 16384 + 256);
+  unsigned char* wtc = c.take<unsigned char>((size_t)(1 + 2 * (smct::FF / smct::FD)) * 16384 + 256 + 2048);   // blocks, header, noise-scale table
 
   if (io.loss_sums) SMCT_CUDA(cudaMemsetAsync(io.loss_sums, 0, 8 * sizeof(double), st));
   if (use_tc) {
-    smct::TcAttnPrep ap{pr.Wq, pr.bq, pr.Wk, pr.bk, pr.Wv, pr.bv, pr.logvar_q, pr.logvar_k, pr.logvar_v, s.logvar_dim};
+    smct::TcAttnPrep ap{pr.Wq, pr.bq, pr.Wk, pr.bk, pr.Wv, pr.bv, pr.logvar_q, pr.logvar_k, pr.logvar_v, pr.logvar_z, s.logvar_dim};
     smct::tc_weight_prep_kernel<<<1, 1024, 0, st>>>(pr.Wz, pr.W1, pr.W2, pr.b1, pr.ln1_g, pr.ln1_b, s.dff, wtc, ap);
     SMCT_LAUNCH_CHECK("tc_weight_prep_kernel");
   }
@@ -388,8 +390,15 @@ int forward_fused(const smct_shape& s, const smct_params& pr, const smct_io& io,
                                    (int)sizeof(smct::FusedSmem)));
     SMCT_CUDA(cudaFuncSetAttribute(smct::fused_tc_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)sizeof(smct::FusedTcSmem) + 1024));
+    SMCT_CUDA(cudaFuncSetAttribute(smct::fused2_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)sizeof(smct::Fused2Smem) + 128));
+    SMCT_CUDA(cudaFuncSetAttribute(smct::fused2_forward_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                   cudaSharedmemCarveoutMaxShared));
   }
-  if (use_tc) {
+  if (algo == SMCT_ALGO_FUSED) {
+    smct::fused2_forward_kernel<<<B, smct::F2NT, sizeof(smct::Fused2Smem) + 128, st>>>(a);
+    SMCT_LAUNCH_CHECK("fused2_forward_kernel");
+  } else if (use_tc) {
     smct::fused_tc_forward_kernel<<<B, smct::FNT, sizeof(smct::FusedTcSmem) + 1024, st>>>(a);
     SMCT_LAUNCH_CHECK("fused_tc_forward_kernel");
   } else {
@@ -512,11 +521,13 @@ int smct_forward(const smct_shape* shape, const smct_params* params, const smct_
   if (!workspace) return fail(SMCT_ERR_WORKSPACE, "workspace is NULL");
   cudaStream_t st = (cudaStream_t)stream;
   int algo = shape->algo;
-  if (algo == SMCT_ALGO_AUTO) algo = smct::fused_supported(*shape, *io) ? SMCT_ALGO_FUSED : SMCT_ALGO_STAGED;
-  if (algo == SMCT_ALGO_FUSED || algo == SMCT_ALGO_FUSED_FFMA) {
-    if (!smct::fused_supported(*shape, *io)) return fail(SMCT_ERR_UNSUPPORTED, "fused forward does not support this shape/io");
+  if (algo == SMCT_ALGO_AUTO)
+    algo = smct::fused2_supported(*shape, *io) ? SMCT_ALGO_FUSED : (smct::fused_supported(*shape, *io) ? SMCT_ALGO_FUSED_V1 : SMCT_ALGO_STAGED);
+  if (algo == SMCT_ALGO_FUSED || algo == SMCT_ALGO_FUSED_FFMA || algo == SMCT_ALGO_FUSED_V1) {
+    const bool ok = algo == SMCT_ALGO_FUSED ? smct::fused2_supported(*shape, *io) : smct::fused_supported(*shape, *io);
+    if (!ok) return fail(SMCT_ERR_UNSUPPORTED, "fused forward does not support this shape/io");
     if (!io->y) return fail(SMCT_ERR_INVALID, "y (targets) required");
-    return forward_fused(*shape, *params, *io, workspace, workspace_bytes, st, algo == SMCT_ALGO_FUSED);
+    return forward_fused(*shape, *params, *io, workspace, workspace_bytes, st, algo);
   }
   // the per-sequence single-launch variant serves shapes with one particle tile per sequence (P <= 32), where the staged
   // loop is launch-bound (measured on B200: C1 0.69 -> 0.45 ms; with several tiles per sequence it serialises them: slower)

@@ -1,4 +1,4 @@
-// smct_common.cuh — shared device helpers: warp/block reductions, Philox4x32-10 + Box-Muller,
+// smct_common.cuh — shared device helpers: warp/block reductions, Philox4x32-7 + Box-Muller,
 // LayerNorm (Keras non-fused form).  sm_100a only.
 #pragma once
 #include <cuda_runtime.h>
@@ -48,15 +48,19 @@ __device__ __forceinline__ float block_max(float v, float* scratch) {
 }
 
 // ------------------------------------------------------------------------------------------
-// Philox4x32-10 (Salmon et al. SC'11).  Stream layout documented in oracle/philox.py:
+// Philox4x32-R (Salmon et al. SC'11).  Stream layout documented in oracle/philox.py:
 //   key = (seed_lo, seed_hi); counter = (group_lo, group_hi, stream, t)
+// R = 7 rounds: the smallest round count the Random123 authors report as passing BigCrush ("Philox4x32-7"); the noise
+// generation is 256 normals per particle-step and was 15 % of the fused forward with the 10-round default.
+// oracle/philox.py restates the same generator (ROUNDS must match).
 // ------------------------------------------------------------------------------------------
 struct u32x4 { uint32_t x, y, z, w; };
+constexpr int SMCT_PHILOX_ROUNDS = 7;
 
-__device__ __forceinline__ u32x4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
-                                               uint32_t k0, uint32_t k1) {
+__device__ __forceinline__ u32x4 philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                            uint32_t k0, uint32_t k1) {
 #pragma unroll
-  for (int r = 0; r < 10; ++r) {
+  for (int r = 0; r < SMCT_PHILOX_ROUNDS; ++r) {
     const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
     const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
     const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
@@ -81,7 +85,7 @@ __device__ __forceinline__ void box_muller(uint32_t xa, uint32_t xb, float& n0, 
 // four standard normals of group `grp` (64-bit) in stream `which` at timestep t
 __device__ __forceinline__ void philox_normal4(uint64_t seed, uint32_t which, uint32_t t, uint64_t grp,
                                                float n[4]) {
-  const u32x4 x = philox4x32_10((uint32_t)grp, (uint32_t)(grp >> 32), which, t, (uint32_t)seed,
+  const u32x4 x = philox4x32((uint32_t)grp, (uint32_t)(grp >> 32), which, t, (uint32_t)seed,
                                 (uint32_t)(seed >> 32));
   box_muller(x.x, x.y, n[0], n[1]);
   box_muller(x.z, x.w, n[2], n[3]);
@@ -97,7 +101,7 @@ __device__ __forceinline__ float philox_normal1(uint64_t seed, uint32_t which, u
 }
 
 __device__ __forceinline__ double philox_uniform(uint64_t seed, uint32_t t, uint64_t bp) {
-  const u32x4 x = philox4x32_10((uint32_t)bp, (uint32_t)(bp >> 32), 4u, t, (uint32_t)seed,
+  const u32x4 x = philox4x32((uint32_t)bp, (uint32_t)(bp >> 32), 4u, t, (uint32_t)seed,
                                 (uint32_t)(seed >> 32));
   return ((double)(x.x >> 5) * 67108864.0 + (double)(x.y >> 6)) * 1.1102230246251565e-16;  // 2^-53
 }

@@ -631,7 +631,7 @@ inline size_t fused_forward_ws(const smct_shape& s) {
   n += 2 * fused_align((size_t)s.B * s.P * Sa * sizeof(unsigned short));
   n += fused_align((size_t)s.B * s.P * sizeof(unsigned short));
   n += fused_align((size_t)s.B * sizeof(int));
-  n += fused_align((size_t)(1 + 2 * (FF / FD)) * 16384 + 256);   // tensor-core weight blocks + header
+  n += fused_align((size_t)(1 + 2 * (FF / FD)) * 16384 + 256 + 2048);   // tensor-core weight blocks + header + noise-scale table
   return n + 1024;
 }
 

@@ -63,11 +63,6 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float v[16]) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// four consecutive per-column constants (16-byte aligned shared arrays) with one 128-bit load
-__device__ __forceinline__ void ld4(const float* p, float v[4]) {
-  const float4 t = *reinterpret_cast<const float4*>(p);
-  v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
-}
 
 __global__ void __launch_bounds__(FNT, 1) fused_tc_forward_kernel(const FusedArgs a) {
   extern __shared__ unsigned char smem_raw_tc[];

@@ -212,10 +212,16 @@ struct TcHeader {
   float pad2[3];
 };
 
-struct TcAttnPrep {     // optional inputs for the attention operand scales
-  const float *Wq, *bq, *Wk, *bk, *Wv, *bv, *logvar_q, *logvar_k, *logvar_v;
+struct TcAttnPrep {     // optional inputs for the attention operand scales and the noise-scale table
+  const float *Wq, *bq, *Wk, *bk, *Wv, *bv, *logvar_q, *logvar_k, *logvar_v, *logvar_z;
   int logvar_dim;
 };
+
+// four consecutive per-column constants (16-byte aligned) with one 128-bit load
+__device__ __forceinline__ void ld4(const float* p, float v[4]) {
+  const float4 t = *reinterpret_cast<const float4*>(p);
+  v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
 
 __global__ void __launch_bounds__(1024) tc_weight_prep_kernel(const float* Wz, const float* W1, const float* W2,
                                                               const float* b1, const float* ln_g, const float* ln_b,
@@ -281,6 +287,15 @@ __global__ void __launch_bounds__(1024) tc_weight_prep_kernel(const float* Wz, c
     h->s_q = ldexpf(qs, eq); h->s_k = ldexpf(1.f, ek); h->s_v = ldexpf(1.f, ev);
     h->inv_qk = ldexpf(1.f, -(eq + ek)); h->inv_v = ldexpf(1.f, -ev);
     h->pad2[0] = h->pad2[1] = h->pad2[2] = 0.f;
+  }
+  if (ap.Wq && ap.logvar_z && tid < 4 * 64) {
+    // noise-scale table behind the header (+256 B): [which][d] = exp(logvar/2) for k,q,v,z, then exp(-logvar) for k,q,v,z
+    float* tab = reinterpret_cast<float*>(out + (size_t)nblk * 2 * tc::B_PART_BYTES + 256);
+    const int which = tid >> 6, d = tid & 63;
+    const float* lv = which == 0 ? ap.logvar_k : (which == 1 ? ap.logvar_q : (which == 2 ? ap.logvar_v : ap.logvar_z));
+    const float v = lv[ap.logvar_dim > 1 ? d : 0];
+    tab[which * 64 + d] = expf(0.5f * v);
+    tab[(4 + which) * 64 + d] = expf(-v);
   }
   __syncthreads();
   for (int idx = tid; idx < nblk * 4096; idx += 1024) {

@@ -183,7 +183,9 @@ class SMC_Transformer:
         eps_t = cvt(eps, torch.float32)
         out = F.forward(shape, params, x, y, eps=eps_t, u=cvt(u, torch.float64), i_forced=cvt(i_forced, torch.int32),
                         seed=seed, want=want)
-        self._last_forward = dict(shape=shape, params=params, x=x, y=y, out=out, eps=eps_t, seed=seed)
+        # the log-variances the forward USED (an EM update overwrites the variables in place before the backward runs)
+        logvar_fwd = {n: params[n].clone() for n in ("logvar_k", "logvar_q", "logvar_v", "logvar_z")}
+        self._last_forward = dict(shape=shape, params=params, x=x, y=y, out=out, eps=eps_t, seed=seed, logvar_fwd=logvar_fwd)
         self.cell.dec_timestep = 0   # SMC_Transformer.py:214-215
         self.cell.cell_count = 0
         self.noise_K_resampled = out["noise_K"]

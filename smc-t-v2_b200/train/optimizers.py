@@ -16,8 +16,9 @@ class CustomSchedule:
         self.warmup_steps = warmup_steps
 
     def __call__(self, step):
-        step = max(float(step), 1.0)
-        return self.d_model ** -0.5 * min(step ** -0.5, step * self.warmup_steps ** -1.5)
+        step = float(step)
+        arg1 = step ** -0.5 if step > 0 else float("inf")   # tf.math.rsqrt(0) = inf; min() picks arg2 = 0: lr(0) = 0
+        return self.d_model ** -0.5 * min(arg1, step * self.warmup_steps ** -1.5)
 
 
 class Adam:
@@ -34,9 +35,12 @@ class Adam:
 
     def apply_gradients(self, grads_and_vars):
         """grads_and_vars: iterable of (grad tensor, parameter tensor) — parameters are updated in place."""
+        # tf.keras: the schedule is evaluated at the PRE-increment `iterations`; iterations + 1 only enters the bias
+        # correction (optimizer_v2 _prepare_local / adam.py) — so the first update of CustomSchedule has lr = 0
+        lr = self._lr()
         self.iterations += 1
         t = self.iterations
-        lr_t = self._lr() * math.sqrt(1.0 - self.beta_2 ** t) / (1.0 - self.beta_1 ** t)
+        lr_t = lr * math.sqrt(1.0 - self.beta_2 ** t) / (1.0 - self.beta_1 ** t)
         for g, p in grads_and_vars:
             if g is None:
                 continue

@@ -218,7 +218,7 @@ def test_forward_c4_particle_count(name, algo):
 FUSED_WANT = ("i_out", "logw", "noise_q", "noise_z", "noise_K", "noise_V", "loss_sums")
 
 
-FUSED_ALGOS = ["fused", "fused_ffma"]
+FUSED_ALGOS = ["fused", "fused_v1", "fused_ffma"]
 
 
 @pytest.mark.parametrize("algo", FUSED_ALGOS)

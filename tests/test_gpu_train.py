@@ -1,0 +1,144 @@
+"""The `run.py -algo smc_t` switch: SMCTAlgo(dataset, args).train() — mirror of /root/reference/src/algos/run_SMC_T.py:16-47,
+121-153, src/train/train_functions.py:146-243, src/scripts/run.py:128-135 — plus the training-step corner cases
+(EM with an optimiser, classification inputs)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+class TinyDataset:
+    """A Dataset-like object with the reference's protocol (data_provider/class_datasets.py:10-93): get_datasets() ->
+    (train, val, test) arrays; data_to_dataset(...) -> iterables of (inputs, targets, attention_mask) batches."""
+    name = "synthetic"
+
+    def __init__(self, B=8, S=12, F=1, n_train=4, n_val=2, classification=False, vocab=12):
+        from smct_b200 import utils
+        self.seq_len, self.B, self.F = S, B, F
+        self.classification = classification
+        self.output_size = vocab if classification else F
+        rng = np.random.default_rng(0)
+        if classification:
+            self.data = rng.integers(1, vocab, size=((n_train + n_val + 1) * B, S + 1, 1)).astype(np.int32)
+        else:
+            x, y = utils.synthetic_ar1((n_train + n_val + 1) * B, S, F, alpha=0.8, var=0.5)
+            self.data = np.concatenate([x, y[:, -1:]], axis=1)
+        self.n_train, self.n_val = n_train, n_val
+
+    def get_datasets(self):
+        B = self.B
+        a, b = self.n_train * B, (self.n_train + self.n_val) * B
+        return self.data[:a], self.data[a:b], self.data[b:]
+
+    def _batches(self, data):
+        out = []
+        for i in range(0, len(data), self.B):
+            d = data[i:i + self.B]
+            inp, tar = d[:, None, :-1, :], d[:, None, 1:, :]       # (B,1,S,F): split of class_datasets.py:19-22
+            out.append((inp, tar, None))
+        return out
+
+    def data_to_dataset(self, train_data, val_data, test_data, num_dim=4):
+        assert num_dim == 4
+        return self._batches(train_data), self._batches(val_data), self._batches(test_data)
+
+
+def test_smct_algo_train_two_epochs(tmp_path):
+    """algos["smc_t"](dataset, args).train(): 2 epochs, history / CSV / weights written, the loss drops."""
+    from smct_b200.algos.run_SMC_T import algos, default_args
+    ds = TinyDataset()
+    args = default_args(d_model=8, dff=8, particles=10, sigmas=0.5, ep=2, bs=8, output_path=str(tmp_path))
+    algo = algos["smc_t"](dataset=ds, args=args)
+    assert algo.optimizer is not None and algo.EPOCHS == 2 and algo.seq_len == 12
+    algo.smc_transformer.seed = 11                      # same draws in every step: the loss is a function of the weights only
+    algo.optimizer.learning_rate = 5e-3                 # CustomSchedule starts at ~1e-6: too slow to see in 8 steps
+    w0 = algo.smc_transformer.cell.ffn.dense1.kernel.numpy().copy()
+    hist = algo.train()
+    assert len(hist["train_loss"]) == 2 and len(hist["val_loss"]) == 2 and len(hist["train_mse_metric"]) == 2
+    assert np.all(np.isfinite(hist["train_loss"])) and np.all(np.isfinite(hist["val_loss"]))
+    assert hist["train_loss"][1] < hist["train_loss"][0], hist
+    assert not np.array_equal(algo.smc_transformer.cell.ffn.dense1.kernel.numpy(), w0)
+    assert algo.optimizer.iterations == 8
+    out = algo.out_folder
+    assert os.path.exists(os.path.join(out, "model.npz")) and os.path.exists(os.path.join(out, "smc_t_history_1.csv"))
+    assert os.path.exists(os.path.join(out, "config.json")) and os.path.exists(os.path.join(out, "logvar_after_training.json"))
+    with open(os.path.join(out, "logvar_after_training.json")) as f:
+        assert set(json.load(f)) == {"k", "q", "v", "z"}
+    with pytest.raises(NotImplementedError):
+        algo.test(test_samples=None, temp=1.)
+
+
+def test_smct_algo_default_schedule_runs():
+    """The reference's own optimiser wiring (Adam(CustomSchedule(d_model), 0.9, 0.98, 1e-9)): first update has lr(0) = 0."""
+    from smct_b200.algos.run_SMC_T import SMCTAlgo, default_args
+    from smct_b200.train.optimizers import CustomSchedule
+    assert CustomSchedule(8)(0) == 0.0
+    assert abs(CustomSchedule(8)(4000) - 8 ** -0.5 * 4000 ** -0.5) < 1e-12
+    ds = TinyDataset(n_train=2, n_val=1)
+    algo = SMCTAlgo(dataset=ds, args=default_args(d_model=8, dff=8, particles=5, sigmas=0.1, ep=1, bs=8))
+    w0 = algo.smc_transformer.cell.ffn.dense1.kernel.numpy().copy()
+    from smct_b200.train.train_step_functions import train_step_SMC_T
+    inp, tar, _ = algo.train_dataset[0]
+    train_step_SMC_T(inp, tar, algo.smc_transformer, algo.optimizer, it=1)
+    assert np.array_equal(algo.smc_transformer.cell.ffn.dense1.kernel.numpy(), w0)      # lr(0) = 0, like tf.keras
+    train_step_SMC_T(inp, tar, algo.smc_transformer, algo.optimizer, it=2)
+    assert not np.array_equal(algo.smc_transformer.cell.ffn.dense1.kernel.numpy(), w0)
+    assert algo.out_folder is None
+
+
+def test_train_step_with_EM_and_optimizer():
+    """EM mode: the log-variances are not trainable (Adam must not touch them), EM overwrites them before the loss, and
+    the backward replays the forward with the variances the forward used."""
+    from smct_b200.algos.run_SMC_T import SMCTAlgo, default_args
+    from smct_b200.train.optimizers import Adam
+    from smct_b200.train.train_step_functions import compute_gradients, train_step_SMC_T
+    ds = TinyDataset(n_train=1, n_val=1)
+    algo = SMCTAlgo(dataset=ds, args=default_args(d_model=8, dff=8, particles=6, sigmas=0.5, EM_param=0.6, ep=1, bs=8))
+    m = algo.smc_transformer
+    att = m.cell.attention_smc
+    assert not att.logvar_k.trainable and all(v.name[:6] != "logvar" for v in m.trainable_variables)
+    m.seed = 3
+    inp, tar, _ = ds._batches(ds.data[:8])[0]
+    opt = Adam(1e-2)
+    lv0 = {n: float(getattr(att, "logvar_" + n).numpy()) for n in "kqvz"}
+    loss, _ = train_step_SMC_T(inp, tar, m, opt, it=2, EM_param=0.6)
+    lv1 = {n: float(getattr(att, "logvar_" + n).numpy()) for n in "kqvz"}
+    assert all(lv1[n] != lv0[n] for n in "kqvz")                       # moved by EM ...
+    # ... and by EM only: redo the EM update by hand from the recorded noises
+    from smct_b200.train.utils import EM_update
+    for n, noise in (("k", m.noise_K_resampled), ("q", m.noise_q), ("v", m.noise_V_resampled), ("z", m.noise_z)):
+        cur = lv0[n]
+        for j in range(noise.shape[0]):
+            cur = EM_update(float(noise[j].double().square().mean()), cur, 2, 0.6)
+        assert abs(cur - lv1[n]) < 1e-5 * max(1.0, abs(cur)), (n, cur, lv1[n])
+    assert len(opt._slots) == len(m.trainable_variables)
+    # the gradient belongs to the forward that was run: the q / z noises are regenerated with the forward's variances
+    fwd = m._last_forward
+    assert abs(float(fwd["logvar_fwd"]["logvar_q"]) - lv0["q"]) < 1e-7
+    g = compute_gradients(m, inp, tar)
+    assert all(torch.isfinite(v).all() for v in g.values())
+
+
+def test_classification_train_step():
+    """The nlp checkout's inputs (integer tokens): training needs the regression-era noise_z; the error comes BEFORE the
+    forward, and with noise_z_mode = "pyc" the step trains."""
+    from smct_b200.algos.run_SMC_T import SMCTAlgo, default_args
+    from smct_b200.train.optimizers import Adam
+    from smct_b200.train.train_step_functions import train_step_SMC_T
+    ds = TinyDataset(classification=True, n_train=1, n_val=1)
+    algo = SMCTAlgo(dataset=ds, args=default_args(d_model=16, dff=16, particles=6, sigmas=0.1, ep=1, bs=8))
+    m = algo.smc_transformer
+    inp, tar, _ = algo.train_dataset[0]
+    opt = Adam(1e-2)
+    m._last_forward = None
+    with pytest.raises(NotImplementedError, match="noise_z_mode"):
+        train_step_SMC_T(inp, tar, m, opt, it=1)
+    assert m._last_forward is None                                     # no forward was run
+    m.noise_z_mode = "pyc"
+    m.seed = 5
+    losses = [float(train_step_SMC_T(inp, tar, m, opt, it=i + 1)[0]) for i in range(6)]
+    assert np.all(np.isfinite(losses)) and losses[-1] < losses[0], losses
