@@ -9,9 +9,14 @@ the ancestor gather) over one batch of the workload.  Workload at N=1: BASELINE.
 (bs=4096, particles=1024, d_model=64, dff=256, seq_len=128), processed in resident chunks because the
 K/V/R state of the whole batch (412 GB) exceeds one GPU's HBM.  With N>1 every rank runs the same
 per-GPU batch on its own sequences (weak scaling; the forward needs no collective — all particles of
-a sequence live on one GPU).  Prints ONE JSON line on rank 0.
+a sequence live on one GPU).  Prints ONE JSON line on rank 0.  Besides the contract keys the line carries
+  other_shapes  BASELINE.json configs[0..2] (the reference's own shapes), one CUDA-event-timed forward each
+  train         configs[4]: one optimiser step (forward + smct_backward + NCCL gradient all-reduce + Adam) on a
+                resident shard per GPU, the all-reduce inside the timed region
+  e2e           host buffers in, pred / pred_resampl / w back in pinned host memory (and a loss-only variant)
 """
 import argparse
+import ctypes
 import json
 import os
 import statistics
@@ -47,10 +52,12 @@ def parse():
     ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=None, help="override the per-GPU batch (debug)")
     ap.add_argument("--chunk", type=int, default=None, help="sequences per resident chunk")
-    ap.add_argument("--algo", default="auto", choices=["auto", "staged", "fused", "fused_ffma"])
+    ap.add_argument("--algo", default="auto", choices=["auto", "staged", "fused", "fused_v1", "fused_ffma", "staged_seq"])
     ap.add_argument("--cpu-sample", type=int, default=None, help="sequences in the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the other_shapes and train sub-records")
+    ap.add_argument("--train-batch", type=int, default=None, help="sequences per GPU in the train sub-record")
     ap.add_argument("--sigma2", type=float, default=0.5, help="variance of the k,q,v,z noises (run.py default 0.5)")
     ap.add_argument("--sigma-obs", type=float, default=0.5, help="observation variance of the Gaussian weights")
     return ap.parse_args()
@@ -118,8 +125,9 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------------
 # CPU arm: reference-equivalent eager restatement (oracle/ref_eager_torch.py) on the host cores
 # --------------------------------------------------------------------------------------------------
-def cpu_reference_run(wl, sample_B, steps, warmup, sigma2=0.5, sigma_obs=0.5):
-    """Times the reference-equivalent CPU path.  The only place bench.py executes oracle/ code."""
+def cpu_reference_run(wl, sample_B, steps, warmup, sigma2=0.5, sigma_obs=0.5, warmup_B=None):
+    """Times the reference-equivalent CPU path.  The only place bench.py executes oracle/ code.
+    `warmup` untimed steps run on `warmup_B` sequences (default: the sample size)."""
     import torch
     from oracle import ref_eager_torch as E
     from oracle import smct_oracle as O
@@ -128,45 +136,56 @@ def cpu_reference_run(wl, sample_B, steps, warmup, sigma2=0.5, sigma_obs=0.5):
     _, P, S, D, dff, F, alpha, var = WORKLOADS[wl]
     cores = len(os.sched_getaffinity(0))
     torch.set_num_threads(cores)
-    cfg = O.Config(B=sample_B, P=P, S=S, D=D, dff=dff, F_x=F, F_y=F, sigma_obs=sigma_obs)
     p = utils.init_parameters(D, dff, F, F, sigma2=sigma2)
     tp = {k: torch.from_numpy(v.reshape(()) if k.startswith("logvar") else v) for k, v in p.items()}
-    x, y = utils.synthetic_ar1(sample_B, S, F, alpha, var)
-    tx, ty = torch.from_numpy(x), torch.from_numpy(y)
     gen = torch.Generator().manual_seed(0)
-    times = []
-    for i in range(warmup + steps):
+
+    def one(nB):
+        cfg = O.Config(B=nB, P=P, S=S, D=D, dff=dff, F_x=F, F_y=F, sigma_obs=sigma_obs)
+        x, y = utils.synthetic_ar1(nB, S, F, alpha, var)
+        tx, ty = torch.from_numpy(x), torch.from_numpy(y)
         t0 = time.perf_counter()
         out = E.forward(cfg, tp, tx, ty, generator=gen)
         float(E.loss_pyc(cfg, tp, out, ty))
-        dt = time.perf_counter() - t0
-        if i >= warmup:
-            times.append(dt)
+        return time.perf_counter() - t0
+
+    wB = warmup_B or sample_B
+    for _ in range(warmup):
+        one(wB)
+    times = [one(sample_B) for _ in range(steps)]
     t = sum(times) / len(times)
     return {"value": sample_B * P * S / t, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": "%d of the workload's sequences per step (B=%d, P=%d, S=%d, D=%d, dff=%d), %d timed step(s) after %d "
-                      "warm-up; op-for-op torch-CPU restatement of the reference's eager TF algorithm "
-                      "(TensorFlow is not installed)" % (sample_B, sample_B, P, S, D, dff, steps, warmup),
+            "sample": "%d of the workload's sequences per step (B=%d, P=%d, S=%d, D=%d, dff=%d; linear in B: sequences are "
+                      "independent), %d timed step(s) after %d warm-up step(s) of B=%d; op-for-op torch-CPU restatement of the "
+                      "reference's eager TF algorithm (TensorFlow is not installed)" % (sample_B, sample_B, P, S, D, dff, steps,
+                                                                                         warmup, wB),
             "s_per_step": t}
 
 
 def default_cpu_sample(wl):
-    return {"c4": 1, "c3": 16, "c2": 32, "c1": 32}[wl]
+    return {"c4": 8, "c3": 16, "c2": 32, "c1": 32}[wl]   # C4 at a reduced batch (B=8), C1-C3 near full
 
 
 def run_reference(args):
+    """--impl reference: rank 0 times the CPU port on all host threads; the other ranks exit without work."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     wl = args.workload
     B, P, S, D, dff, F, _, _ = WORKLOADS[wl]
-    sample = args.cpu_sample or default_cpu_sample(wl)
+    want = args.cpu_sample or default_cpu_sample(wl)
+    # size the sample so that the whole --steps/--warmup run ends within a few minutes: probe one sequence first
+    probe = cpu_reference_run(wl, 1, 1, 0, args.sigma2, args.sigma_obs)["s_per_step"]
+    budget_s = 240.0
+    n_runs = args.steps + args.warmup
+    sample = want if args.cpu_sample else int(max(1, min(want, budget_s / max(probe * n_runs, 1e-9))))
     r = cpu_reference_run(wl, sample, args.steps, args.warmup, args.sigma2, args.sigma_obs)
     line = {
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["s_per_step"] * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_desc(wl, B, P, S, D, dff, F, args.sigma2, args.sigma_obs), "sample_sequences_per_step": sample,
+                   "sample_rule": "min(%d, what fits %.0f s for %d steps at the probed %.2f s per sequence)" % (want, budget_s, n_runs, probe),
                    "device": "host CPU, %d threads" % r["cores"]},
         "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -189,13 +208,140 @@ def measured_peak():
 
 
 def ncu_traffic(algo, wl):
-    """dram bytes per forward launch from the committed ncu capture, if one exists for this algo/workload."""
+    """dram bytes of one forward launch from the committed ncu capture (profiles/traffic.json), if one exists for this
+    algo/workload: {"bytes": dram read+write of the capture, "sequences": sequences in the captured launch, ...}."""
     path = os.path.join(ROOT, "profiles", "traffic.json")
     try:
         with open(path) as f:
             return json.load(f).get("%s:%s" % (algo, wl))
     except Exception:
         return None
+
+
+class L2Flusher:
+    """Writes a buffer larger than the 126 MB L2 between timed iterations of the small shapes."""
+
+    def __init__(self, dev, nbytes=256 << 20):
+        import torch
+        self.buf = torch.empty(nbytes // 4, dtype=torch.float32, device=dev)
+        self.v = 0.0
+
+    def __call__(self):
+        self.v += 1.0
+        self.buf.fill_(self.v)
+
+
+def bench_small_shape(wl, args, dev, rank, world, dist, flush, iters=10, warmup=3):
+    """One of the reference's own shapes (BASELINE.json configs[0..2]): every forward timed with its own pair of CUDA
+    events, L2 flushed in between.  At N>1 every rank runs the same per-GPU batch (weak scaling)."""
+    import torch
+    import smct_b200.functional as F_
+    from smct_b200 import utils
+    import smct_b200
+    lib = smct_b200.load_library()
+    B, P, S, D, dff, F, alpha, var = WORKLOADS[wl]
+    p_host = utils.init_parameters(D, dff, F, F, sigma2=args.sigma2)
+    params = {k: torch.as_tensor(v, device=dev) for k, v in p_host.items()}
+    x, y = utils.synthetic_ar1(B, S, F, alpha, var, seed=1234 + rank)
+    xd, yd = torch.as_tensor(x, device=dev), torch.as_tensor(y, device=dev)
+    shape = F_.make_shape(B, P, S, D, dff=dff, F_x=F, F_y=F, algo="auto", b_global0=rank * B, sigma_obs=args.sigma_obs)
+    out = F_.forward(shape, params, xd, yd, seed=1, want=("loss_sums",))
+    for i in range(warmup):
+        F_.forward(shape, params, xd, yd, seed=2 + i, want=("loss_sums",), out=out)
+    torch.cuda.synchronize()
+    lib.smct_launch_count(1)
+    ms = []
+    for i in range(iters):
+        flush()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        F_.forward(shape, params, xd, yd, seed=10 + i, want=("loss_sums",), out=out)
+        e1.record()
+        torch.cuda.synchronize()
+        ms.append(e0.elapsed_time(e1))
+    launches = lib.smct_launch_count(1) // iters
+    t = torch.tensor([statistics.mean(ms)], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    mean_ms = float(t.item())
+    bpp = utils.algorithmic_bytes_per_particle_step(D, S)
+    return {"workload": workload_desc(wl, B, P, S, D, dff, F, args.sigma2, args.sigma_obs), "per_gpu_batch": B,
+            "ms_per_forward": mean_ms, "ms_min": min(ms), "iters": iters,
+            "value": float(B) * P * S * world / (mean_ms * 1e-3), "unit": UNIT, "launches_per_forward": int(launches),
+            "algorithmic_GBs": float(B) * P * S * bpp / (mean_ms * 1e-3) / 1e9,
+            "l2": "flushed between iterations (256 MB write); state %.1f MB" % (3.0 * B * P * S * D * 4 / 1e6)}
+
+
+def bench_train(args, dev, rank, world, dist, n_sm, steps=3, warmup=1):
+    """BASELINE.json configs[4] (C5): one optimiser step of the batch-sharded SMC-T training on a resident C4-shaped shard
+    per GPU: forward (smct_forward) + backward (smct_backward) + NCCL all-reduce of the flat gradient buffer + Adam
+    (smct_adam_step).  Reference: src/train/train_step_functions.py:31-68."""
+    import torch
+    import smct_b200.functional as F_
+    from smct_b200 import utils
+    from smct_b200.train.optimizers import Adam, CustomSchedule
+    _, P, S, D, dff, F, alpha, var = WORKLOADS["c4"]
+    B = args.train_batch or 2 * n_sm          # one wave of the fused forward (two sequences per SM)
+    params = {k: torch.as_tensor(v, device=dev) for k, v in utils.init_parameters(D, dff, F, F, sigma2=args.sigma2).items()}
+    x, y = utils.synthetic_ar1(B, S, F, alpha, var, seed=4321 + rank)
+    xd, yd = torch.as_tensor(x, device=dev), torch.as_tensor(y, device=dev)
+    shape = F_.make_shape(B, P, S, D, dff=dff, F_x=F, F_y=F, noise_z_mode="pyc", algo="auto", b_global0=rank * B,
+                          sigma_obs=args.sigma_obs)
+    opt = Adam(CustomSchedule(D), beta_1=0.9, beta_2=0.98, epsilon=1e-9)
+    names = sorted(params)
+    inv_n = 1.0 / (float(B) * world * P * S)
+    state = {"out": None}
+
+    def step(i):
+        out = F_.forward(shape, params, xd, yd, seed=500 + i, want=("i_out", "loss_sums"), out=state["out"])
+        state["out"] = out
+        grads = F_.backward(shape, params, xd, yd, out, seed=500 + i, inv_n=inv_n)
+        flat = torch.cat([grads[n].reshape(-1) for n in names] + [out["loss_sums"].float()])
+        if dist is not None:
+            dist.all_reduce(flat)          # the gradient exchange: one flat fp32 buffer over NCCL / NVLink
+        o = 0
+        for n in names:
+            k = grads[n].numel()
+            grads[n].copy_(flat[o:o + k].reshape(grads[n].shape))
+            o += k
+        opt.apply_gradients((grads[n], params[n]) for n in names)
+        return flat[o:o + 8]
+
+    for i in range(warmup):
+        step(i)
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        sums = step(warmup + i)
+    e1.record()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    # the forward alone on the same shard, for the split
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    F_.forward(shape, params, xd, yd, seed=999, want=("i_out", "loss_sums"), out=state["out"])
+    f1.record()
+    torch.cuda.synchronize()
+    n = float(B) * world * P * S
+    tot = sums.double().cpu().numpy()
+    state["out"] = None
+    F_.release_workspace()
+    F_._bws_cache.clear()
+    torch.cuda.empty_cache()
+    return {"what": "one optimiser step: smct_forward + smct_backward + NCCL all-reduce of the flat gradient buffer + Adam, "
+                    "resident C4-shaped shard per GPU (BASELINE.json configs[4])",
+            "per_gpu_batch": B, "global_batch": B * world, "ms_per_step": float(t.item()), "forward_ms": f0.elapsed_time(f1),
+            "value": n / (float(t.item()) * 1e-3), "unit": UNIT, "steps": steps, "warmup": warmup,
+            "grad_elems_allreduced": int(sum(params[k].numel() for k in names)) + 8,
+            "allreduce": "inside the timed region (NCCL, %d ranks)" % world if world > 1 else "single rank: no exchange",
+            "loss": float((0.5 * tot[:4].sum() + (0.5 / args.sigma_obs) * tot[4]) / n)}
 
 
 def run_b200(args):
@@ -216,6 +362,16 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = smct_b200.load_library()
     dev = torch.device("cuda", local)
+    n_sm = torch.cuda.get_device_properties(local).multi_processor_count
+
+    # ---------------- sub-records first (they release their memory before the main workload is sized) ----------------
+    other_shapes, train = None, None
+    if not args.no_extras and args.workload == "c4":
+        flush = L2Flusher(dev)
+        other_shapes = {wl: bench_small_shape(wl, args, dev, rank, world, dist, flush) for wl in ("c1", "c2", "c3")}
+        del flush
+        train = bench_train(args, dev, rank, world, dist, n_sm)
+        torch.cuda.empty_cache()
 
     wl = args.workload
     B, P, S, D, dff, F, alpha, var = WORKLOADS[wl]
@@ -236,14 +392,25 @@ def run_b200(args):
     def ws_per_seq(algo):
         s1 = F_.make_shape(1, P, S, D, dff=dff, F_x=F, F_y=F, algo=algo)
         s2 = F_.make_shape(2, P, S, D, dff=dff, F_x=F, F_y=F, algo=algo)
-        import ctypes
         return lib.smct_workspace_bytes(ctypes.byref(s2)) - lib.smct_workspace_bytes(ctypes.byref(s1))
 
     per_seq = state_per_seq + ws_per_seq(args.algo)
     fit = max(1, int((free_b * 0.85 - fixed) // per_seq))
-    n_sm = torch.cuda.get_device_properties(local).multi_processor_count
-    # the fused forward runs one CTA (= one sequence) per SM: size chunks as whole waves of the SM count
-    chunk = args.chunk or (min(B, fit, 4 * n_sm) // n_sm * n_sm if min(B, fit) >= n_sm else min(B, fit))
+    # the persistent forward keeps whole sequences resident on the SMs — two per SM (smct_fused2.cuh), one for the first-
+    # generation kernels: only those algorithms size their chunks as whole waves; the per-stage kernels take what fits
+    fused_shape = (D == 64 and dff % 64 == 0 and 64 <= dff <= 256 and P <= 1024)
+    wave = 0
+    if fused_shape and args.algo in ("auto", "fused"):
+        wave = 2 * n_sm if F <= 4 else n_sm
+    elif fused_shape and args.algo in ("fused_v1", "fused_ffma"):
+        wave = n_sm
+    cap = min(B, fit)
+    if args.chunk:
+        chunk = args.chunk
+    elif wave and cap >= wave:
+        chunk = min(cap, 2 * wave) // wave * wave
+    else:
+        chunk = cap
     n_chunks = (B + chunk - 1) // chunk
 
     pred = torch.empty((B, P, S, F), dtype=torch.float32, device=dev)
@@ -255,7 +422,7 @@ def run_b200(args):
     loss_sums = torch.zeros((n_chunks, 8), dtype=torch.float64, device=dev)
     loss_host = torch.zeros((n_chunks, 8), dtype=torch.float64).pin_memory()
 
-    def forward_all(xd, yd, seed):
+    def forward_all(xd, yd, seed, after_chunk=None):
         for c in range(n_chunks):
             b0, b1 = c * chunk, min(B, (c + 1) * chunk)
             n = b1 - b0
@@ -264,6 +431,8 @@ def run_b200(args):
             out = dict(pred=pred[b0:b1], pred_resampl=pred_r[b0:b1], w=w[b0:b1], K=Kc[:n], V=Vc[:n], R=Rc[:n],
                        loss_sums=loss_sums[c])
             F_.forward(shape, params, xd[b0:b1], yd[b0:b1], seed=seed, want=("loss_sums",), out=out)
+            if after_chunk is not None:
+                after_chunk(b0, b1)
 
     from smct_b200.distributed import loss_from_sums as _loss_from_sums
 
@@ -306,37 +475,72 @@ def run_b200(args):
     value = psteps_per_gpu * world / (total_ms_max * 1e-3)
     loss_dev = loss_from_sums(loss_sums.cpu())
 
-    # ---------------- end-to-end: host buffers -> H2D -> forward -> D2H loss ----------------
+    # ---------------- end-to-end through the public API with HOST buffers ----------------
+    # (a) "outputs": what SMC_Transformer.call hands its caller that fits a host — pred, pred_resampl (B,P,S,F) and the
+    #     filtering weights w (B,P,S) — lands in pinned host memory, chunk by chunk on a copy stream, plus the loss sums;
+    #     (b) "loss_only": the training-style call (inputs in, loss sums out).  K, V, R (137 GB each at C4) exist only per
+    #     resident chunk and are not returned by either.  e2e.value is (a).
     e2e = None
     if not args.no_e2e:
-        e_steps = max(1, min(args.steps, 2))
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t_wall0 = time.perf_counter()
-        e0.record()
-        for i in range(e_steps):
-            xd = x_pin.to(dev, non_blocking=True)
-            yd = y_pin.to(dev, non_blocking=True)
-            forward_all(xd, yd, seed=300 + i)
-            loss_host.copy_(loss_sums, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-            loss_e2e = loss_from_sums(loss_host)
-        e1.record()
-        barrier()
-        wall_ms = (time.perf_counter() - t_wall0) * 1e3
-        e_ms = max(e0.elapsed_time(e1), wall_ms)
-        t2 = torch.tensor([e_ms], dtype=torch.float64, device=dev)
-        if dist is not None:
-            dist.all_reduce(t2, op=dist.ReduceOp.MAX)
-        e2e = {"value": float(B) * P * S * e_steps * world / (float(t2.item()) * 1e-3), "unit": UNIT,
-               "h2d_bytes_per_step": int(x_pin.numel() * 4 + y_pin.numel() * 4),
-               "d2h_bytes_per_step": int(loss_host.numel() * 8), "steps": e_steps, "loss": loss_e2e,
-               "api": "smct_b200.functional.forward -> smct_forward (C-ABI), pinned host inputs, loss sums read back"}
+        e_steps = 5
+        out_bytes = (pred.numel() + pred_r.numel() + w.numel()) * 4
+        host_out = None
+        try:
+            host_out = [torch.empty(t_.shape, dtype=torch.float32).pin_memory() for t_ in (pred, pred_r, w)]
+        except Exception:
+            host_out = None
+        copy_stream = torch.cuda.Stream(device=dev)
+
+        def run_e2e(full):
+            def after(b0, b1):
+                done = torch.cuda.Event()
+                done.record()
+                with torch.cuda.stream(copy_stream):
+                    copy_stream.wait_event(done)
+                    for h, d in zip(host_out, (pred, pred_r, w)):
+                        h[b0:b1].copy_(d[b0:b1], non_blocking=True)
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t_wall0 = time.perf_counter()
+            e0.record()
+            loss_v = None
+            for i in range(e_steps):
+                xd = x_pin.to(dev, non_blocking=True)
+                yd = y_pin.to(dev, non_blocking=True)
+                forward_all(xd, yd, seed=300 + i, after_chunk=after if full else None)
+                loss_host.copy_(loss_sums, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+                copy_stream.synchronize()
+                loss_v = loss_from_sums(loss_host)
+            e1.record()
+            barrier()
+            wall_ms = (time.perf_counter() - t_wall0) * 1e3
+            e_ms = max(e0.elapsed_time(e1), wall_ms)
+            t2 = torch.tensor([e_ms], dtype=torch.float64, device=dev)
+            if dist is not None:
+                dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+            return float(B) * P * S * e_steps * world / (float(t2.item()) * 1e-3), loss_v
+
+        v_loss, loss_e2e = run_e2e(False)
+        h2d = int(x_pin.numel() * 4 + y_pin.numel() * 4)
+        if host_out is not None:
+            v_full, loss_e2e = run_e2e(True)
+            chk = float(host_out[2][:min(B, 4)].sum(1).mean())   # weights of a sequence sum to 1 at every step
+            e2e = {"value": v_full, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(out_bytes + loss_host.numel() * 8),
+                   "steps": e_steps, "loss": loss_e2e, "returns": "pred, pred_resampl (B,P,S,F), w (B,P,S) in pinned host memory + loss sums",
+                   "weights_sum_check": chk,
+                   "loss_only": {"value": v_loss, "d2h_bytes_per_step": int(loss_host.numel() * 8)},
+                   "api": "smct_b200.functional.forward -> smct_forward (C-ABI), pinned host inputs, outputs copied back per chunk on a copy stream"}
+        else:
+            e2e = {"value": v_loss, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(loss_host.numel() * 8),
+                   "steps": e_steps, "loss": loss_e2e, "returns": "loss sums only (pinned host buffers for the outputs could not be allocated)",
+                   "api": "smct_b200.functional.forward -> smct_forward (C-ABI), pinned host inputs"}
+        del host_out
 
     # ---------------- CPU baseline (rank 0, N=1 only) ----------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        r = cpu_reference_run(wl, args.cpu_sample or default_cpu_sample(wl), 1, 0, args.sigma2, args.sigma_obs)
+        r = cpu_reference_run(wl, args.cpu_sample or default_cpu_sample(wl), 1, 1, args.sigma2, args.sigma_obs, warmup_B=1)
         cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
     if rank == 0:
@@ -346,28 +550,33 @@ def run_b200(args):
         alg_bytes_per_launch = float(min(chunk, B)) * P * S * bpp
         achieved = float(B) * P * S * bpp / (total_ms_max / args.steps * 1e-3) / 1e9
         algo_used = args.algo
+        tr = ncu_traffic(algo_used, wl)
+        traffic = None if tr is None else float(tr["bytes"]) * min(chunk, B) / float(tr["sequences"])   # per launch of THIS run's chunk
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_desc(wl, B, P, S, D, dff, F, args.sigma2, args.sigma_obs), "per_gpu_batch": B, "chunk_sequences": chunk,
-                       "chunks_per_step": n_chunks, "algo": algo_used, "rng": "device Philox4x32-10 + Box-Muller",
+                       "chunks_per_step": n_chunks, "algo": algo_used, "rng": "device Philox4x32-7 + Box-Muller",
                        "l2": "working set per chunk (%.1f GB state) >> 126 MB L2; no flush needed" % (chunk * state_per_seq / 1e9),
                        "parallelism": "batch-sharded replicas, no collective in the forward"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic(algo_used, wl), "peak_source": peak_src,
+                         "traffic": traffic, "peak_source": peak_src,
                          # the fused path avoids most of the algorithmic bytes (path storage instead of the ancestor gather):
-                         # frac > 1 is expected; this is the DRAM bandwidth the ncu-measured traffic of one launch amounts to
-                         "traffic_frac_of_peak": (None if ncu_traffic(algo_used, wl) is None or min(chunk, B) != 444 else
-                                                  ncu_traffic(algo_used, wl) / (fwd_ms * 1e-3) / 1e9 / peak),
+                         # frac > 1 is expected; traffic_frac_of_peak is the DRAM bandwidth the ncu-measured traffic amounts to
+                         "traffic_frac_of_peak": None if traffic is None else traffic / (fwd_ms * 1e-3) / 1e9 / peak,
+                         "traffic_source": None if tr is None else tr.get("capture"),
                          "algorithmic_bytes_per_particle_step": bpp, "algorithmic_bytes_per_launch": alg_bytes_per_launch,
-                         "launch": "one smct_forward call over one chunk (%.1f ms avg, CUDA events)" % fwd_ms},
+                         "launch": "one smct_forward call over one chunk (%.1f ms avg, CUDA events; includes the small "
+                                   "prologue and the materialize pass)" % fwd_ms},
             "cpu_baseline": cpu,
             "e2e": e2e,
             "gpu_launches": int(launches),
             "clocks": clocks,
             "step_ms": step_ms,
             "loss": loss_dev,
+            "other_shapes": other_shapes,
+            "train": train,
         }
         print(json.dumps(line), flush=True)
     if dist is not None:

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SMCT_ABI_VERSION 2
+#define SMCT_ABI_VERSION 3
 
 enum {
   SMCT_OK = 0,
@@ -119,6 +119,9 @@ typedef struct smct_io {
 int smct_abi_version(void);
 const char *smct_last_error(void);
 const char *smct_build_info(void);
+/* First 32 hex digits of the sha256 over the sources (csrc/ and this header) the binary was compiled from; the binding
+ * refuses a library whose hash differs from the tree it is loaded from (smc-t-v2_b200/build.py:source_hash). */
+const char *smct_source_hash(void);
 /* Number of CUDA kernels this library has launched in the process (reset!=0: return and zero). */
 long long smct_launch_count(int reset);
 

@@ -358,6 +358,60 @@ def forward(cfg: Config, p, x_in, y, eps=None, u=None, i_forced=None, trace: boo
     return out
 
 
+def forecast_multistep(cfg: Config, p, x_past, y_past, eps, u, obs_noise, past_len, future_len):
+    """Regression-era multi-step forecast (src/eval/inference_functions.py:19-39 in its time-series form, recovered from
+    the shipped .pyc `inference_multistep`): run the particle filter on the observed past with resampling stopped at
+    past_len, then roll forward feeding every particle its own last prediction plus N(0, Sigma_obs) observation noise.
+    With injected draws indexed by the absolute timestep, re-running the whole forward for every future step (what the
+    reference does) and continuing it step by step give the same states, so this loop is one pass.
+
+    x_past (B,past_len,F), y_past (B,past_len,F_y); eps (4,S,B,P,D), u (S,B,P) with S = past_len + future_len;
+    obs_noise (S,B,P,F_y) standard normals (entry t is added to the prediction of step t).
+    Returns preds_future (B,P,future_len,F_y)."""
+    B, P, D = cfg.B, cfg.P, cfg.D
+    S = past_len + future_len
+    assert cfg.F_x == cfg.F_y and cfg.weights == "gaussian" and cfg.full_model and cfg.noise
+    K = np.zeros((B, P, S, D), F32)
+    V = np.zeros((B, P, S, D), F32)
+    R = np.zeros((B, P, S, D), F32)
+    sk, sq, sv, sz = (noise_std(p["logvar_" + n]) for n in ("k", "q", "v", "z"))
+    cfgS = Config(**{**cfg.__dict__, "S": S})
+    W_in, b_in = np.asarray(p["W_in"], F32), np.asarray(p["b_in"], F32)
+    sqrtD = F32(math.sqrt(D))
+    preds = []
+    x_next = None
+    sd_obs = F32(math.sqrt(cfg.sigma_obs))
+    for t in range(S):
+        if t < past_len:
+            xin = np.broadcast_to(np.asarray(x_past, F32)[:, None, t, :], (B, P, cfg.F_x))
+        else:
+            xin = x_next
+        X = ((dense(xin, W_in, b_in)) * sqrtD).astype(F32)                                  # get_encoded_input (pyc)
+        x = layer_norm(X, p["ln1_g"], p["ln1_b"], cfg.ln_eps)
+        k = (dense(x, p["Wk"], p["bk"]) + sk * eps[0, t]).astype(F32)
+        q = (dense(x, p["Wq"], p["bq"]) + sq * eps[1, t]).astype(F32)
+        v = (dense(x, p["Wv"], p["bv"]) + sv * eps[2, t]).astype(F32)
+        K[:, :, t, :] = k
+        V[:, :, t, :] = v
+        z_, _ = attention_step(cfgS, q, K, V, t)
+        z = (dense(z_, p["Wz"], p["bz"]) + sz * eps[3, t]).astype(F32)
+        o = layer_norm(z + x, p["ln1_g"], p["ln1_b"], cfg.ln_eps)
+        h = np.maximum(dense(o, p["W1"], p["b1"]), F32(0))
+        r = layer_norm(dense(h, p["W2"], p["b2"]) + o, p["ln2_g"], p["ln2_b"], cfg.ln_eps)
+        pred_t = dense(r, p["Wo"])
+        R[:, :, t, :] = r
+        if t < past_len:                                                                    # resampling stops at past_len
+            _, logw_hat, _ = compute_w_regression(pred_t, np.asarray(y_past, F32)[:, t], cfg.sigma_obs)
+            i_t = categorical_tf_cpu(logw_hat, u[t])
+            K[:, :, :t + 1] = resample(K[:, :, :t + 1], i_t)
+            V[:, :, :t + 1] = resample(V[:, :, :t + 1], i_t)
+            R[:, :, :t + 1] = resample(R[:, :, :t + 1], i_t)
+        else:
+            preds.append(pred_t)
+        x_next = (pred_t + sd_obs * np.asarray(obs_noise[t], F32)).astype(F32)
+    return np.stack(preds, axis=2)
+
+
 # --------------------------------------------------------------------------------------
 # losses / metrics / EM
 # --------------------------------------------------------------------------------------

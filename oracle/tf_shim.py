@@ -33,22 +33,29 @@ def _t(x, dtype=None):
     return torch.as_tensor(np.asarray(x), dtype=dtype)
 
 
+TRACK_GRADIENTS = False   # set by the gradient-fixture generator: trainable variables become autograd leaves
+
+
 class Variable:
     def __init__(self, initial_value=None, name=None, shape=None, trainable=True, dtype=None):
         self.value = _t(initial_value).clone().to(torch.float32) if not isinstance(initial_value, T) else initial_value.clone()
         self.name = name
         self.trainable = trainable
         self._trainable = trainable
+        if TRACK_GRADIENTS and trainable and self.value.is_floating_point():
+            self.value = self.value.detach().requires_grad_(True)
 
     def numpy(self):
-        return self.value.numpy()
+        return self.value.detach().numpy()
 
     @property
     def shape(self):
         return self.value.shape
 
     def assign(self, v):
-        self.value = _t(v).clone()
+        self.value = _t(v).detach().clone()
+        if TRACK_GRADIENTS and self.trainable and self.value.is_floating_point():
+            self.value.requires_grad_(True)
 
     # arithmetic used on logvar variables
     def __mul__(self, o): return self.value * _t(o)
@@ -99,7 +106,25 @@ def _build_tf(rng: RNG):
     tf.stack = lambda values, axis=0: torch.stack([_t(v) for v in values], dim=axis)
     tf.transpose = lambda x, perm=None: _t(x).permute(*perm) if perm is not None else _t(x).T
     tf.tile = lambda x, multiples: _t(x).repeat(*[int(m) for m in multiples])
-    tf.stop_gradient = lambda x: _t(x)
+    tf.stop_gradient = lambda x: _t(x).detach()
+
+    class GradientTape:
+        """tf.GradientTape over torch autograd: the shim's ops ARE torch ops, so the tape is the autograd graph of the
+        forward that ran inside the `with` block (trainable variables are leaves when TRACK_GRADIENTS is set)."""
+
+        def __init__(self, persistent=False, **kw):
+            self.persistent = persistent
+
+        def __enter__(self):
+            return self
+
+        def __exit__(self, *exc):
+            return False
+
+        def gradient(self, target, sources):
+            vals = [s.value if isinstance(s, Variable) else s for s in sources]
+            return list(torch.autograd.grad(_t(target), vals, allow_unused=True, retain_graph=True))
+    tf.GradientTape = GradientTape
     tf.exp = lambda x: torch.exp(_t(x))
     tf.square = lambda x: torch.square(_t(x))
     tf.scalar_mul = lambda s, x: s * _t(x)

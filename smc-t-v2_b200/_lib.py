@@ -9,7 +9,7 @@ c_f64p = ctypes.POINTER(ctypes.c_double)
 c_i32p = ctypes.POINTER(ctypes.c_int32)
 VP = ctypes.c_void_p
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 OK, ERR_INVALID, ERR_CUDA, ERR_WORKSPACE, ERR_UNSUPPORTED = 0, -1, -2, -3, -4
 WEIGHTS = {"gaussian": 0, "classification": 1}
 NOISE_Z = {"checkout": 0, "pyc": 1}
@@ -66,6 +66,7 @@ def _declare(lib):
         "smct_abi_version": (ctypes.c_int, []),
         "smct_last_error": (ctypes.c_char_p, []),
         "smct_build_info": (ctypes.c_char_p, []),
+        "smct_source_hash": (ctypes.c_char_p, []),
         "smct_launch_count": (ctypes.c_longlong, [ctypes.c_int]),
         "smct_workspace_bytes": (ctypes.c_size_t, [SP]),
         "smct_forward": (ctypes.c_int, [SP, PP, IP, VP, ctypes.c_size_t, VP]),
@@ -104,11 +105,7 @@ def load(build_if_needed=True):
         return _lib
     path = _build.LIB
     if build_if_needed:
-        try:
-            _build.build()
-        except Exception:
-            if not os.path.exists(path):
-                raise
+        _build.build()   # no-op when the embedded source hash matches the tree; a compile error or a stale binary without nvcc raises
     if not os.path.exists(path):
         raise RuntimeError("libsmct_b200.so is not built (%s); run `python smc-t-v2_b200/build.py`. "
                            "There is no CPU fallback." % path)
@@ -116,6 +113,10 @@ def load(build_if_needed=True):
     lib._smct_signatures = _declare(lib)
     if lib.smct_abi_version() != ABI_VERSION:
         raise RuntimeError("libsmct_b200.so ABI %d != binding ABI %d" % (lib.smct_abi_version(), ABI_VERSION))
+    have, want = lib.smct_source_hash().decode(), _build.source_hash()
+    if have != want:
+        raise RuntimeError("libsmct_b200.so was built from other sources (embedded hash %s, tree %s); run "
+                           "`python smc-t-v2_b200/build.py --force`" % (have, want))
     _lib = lib
     return lib
 

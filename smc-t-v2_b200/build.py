@@ -25,11 +25,35 @@ def _deps():
     return deps
 
 
-def needs_build():
+def source_hash():
+    """sha256 over the library's sources (csrc/* and include/smct.h, by file name and content).  The hash is compiled
+    into the .so (smct_source_hash()) so that a binary can be matched to the tree it was built from."""
+    import hashlib
+    h = hashlib.sha256()
+    for d in sorted(_deps()):
+        h.update(os.path.basename(d).encode() + b"\0")
+        with open(d, "rb") as f:
+            h.update(f.read())
+        h.update(b"\0")
+    return h.hexdigest()[:32]
+
+
+def built_hash():
+    """Source hash embedded in the existing .so (read from the binary's bytes: no dlopen), or None."""
     if not os.path.exists(LIB):
-        return True
-    t = os.path.getmtime(LIB)
-    return any(os.path.getmtime(d) > t for d in _deps())
+        return None
+    with open(LIB, "rb") as f:
+        blob = f.read()
+    tag = b"smct-source-hash:"
+    i = blob.find(tag)
+    if i < 0:
+        return None
+    return blob[i + len(tag):i + len(tag) + 32].decode("ascii", "replace")
+
+
+def needs_build():
+    """True when there is no library or it was compiled from different sources (hash, not mtime)."""
+    return built_hash() != source_hash()
 
 
 def build(force=False, verbose=False):
@@ -38,10 +62,9 @@ def build(force=False, verbose=False):
         return LIB
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
-        if os.path.exists(LIB):
-            return LIB  # GPU box without a toolchain: use the prebuilt library that travelled with the snapshot
-        raise RuntimeError("nvcc not found and libsmct_b200.so is not built")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB] + SOURCES
+        raise RuntimeError("libsmct_b200.so is missing or was built from other sources (embedded hash %s, tree %s) and nvcc "
+                           "is not available to rebuild it" % (built_hash(), source_hash()))
+    cmd = [nvcc] + NVCC_FLAGS + ['-DSMCT_SOURCE_HASH="%s"' % source_hash(), "-o", LIB] + SOURCES
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     log = os.path.join(HERE, "build.log")
     with open(log, "w") as f:

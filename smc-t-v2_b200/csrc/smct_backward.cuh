@@ -666,7 +666,7 @@ __global__ void __launch_bounds__(128) bwd_rows_kernel(const BwdArgs a) {
       }
       for (int d = tid; d < D; d += 128) rep[a.lay.b_in + d] += dX[d] * a.sqrtD;
     } else if (a.input_mode == SMCT_INPUT_EMBEDDING) {
-      const int tok = ((const int*)a.x_in)[row];
+      const int tok = clamp_index(((const int*)a.x_in)[row], a.Fx);
       for (int d = tid; d < D; d += 128) rep[a.lay.W_in + (long long)tok * D + d] += dX[d] * a.sqrtD;
     }
   }

@@ -18,6 +18,10 @@
 #include "smct_fused2.cuh"
 #include "smct_backward.cuh"
 
+#ifndef SMCT_SOURCE_HASH   // set by smc-t-v2_b200/build.py: sha256 over csrc/ and include/smct.h
+#define SMCT_SOURCE_HASH "unhashed-build------------------"
+#endif
+
 namespace {
 
 thread_local std::string g_last_error;
@@ -390,13 +394,24 @@ int forward_fused(const smct_shape& s, const smct_params& pr, const smct_io& io,
                                    (int)sizeof(smct::FusedSmem)));
     SMCT_CUDA(cudaFuncSetAttribute(smct::fused_tc_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)sizeof(smct::FusedTcSmem) + 1024));
-    SMCT_CUDA(cudaFuncSetAttribute(smct::fused2_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)sizeof(smct::Fused2Smem) + 128));
-    SMCT_CUDA(cudaFuncSetAttribute(smct::fused2_forward_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                   cudaSharedmemCarveoutMaxShared));
   }
   if (algo == SMCT_ALGO_FUSED) {
-    smct::fused2_forward_kernel<<<B, smct::F2NT, sizeof(smct::Fused2Smem) + 128, st>>>(a);
+    // compile-time variants: injected eps (tests) | per-dimension log-variances | the checkout's noise_z
+    using KernelT = void (*)(const smct::FusedArgs);
+    static const KernelT variants[8] = {
+        smct::fused2_forward_kernel<false, false, false>, smct::fused2_forward_kernel<false, false, true>,
+        smct::fused2_forward_kernel<false, true, false>,  smct::fused2_forward_kernel<false, true, true>,
+        smct::fused2_forward_kernel<true, false, false>,  smct::fused2_forward_kernel<true, false, true>,
+        smct::fused2_forward_kernel<true, true, false>,   smct::fused2_forward_kernel<true, true, true>};
+    static PerDeviceOnce f2_once;
+    if (f2_once.need()) {
+      for (KernelT k : variants) {
+        SMCT_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(smct::Fused2Smem) + 128));
+        SMCT_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+      }
+    }
+    const int vi = (io.eps ? 4 : 0) | (s.logvar_dim > 1 ? 2 : 0) | (s.noise_z_mode == SMCT_NOISE_Z_CHECKOUT ? 1 : 0);
+    variants[vi]<<<B, smct::F2NT, sizeof(smct::Fused2Smem) + 128, st>>>(a);
     SMCT_LAUNCH_CHECK("fused2_forward_kernel");
   } else if (use_tc) {
     smct::fused_tc_forward_kernel<<<B, smct::FNT, sizeof(smct::FusedTcSmem) + 1024, st>>>(a);
@@ -500,7 +515,12 @@ const char* smct_build_info(void) {
 #define SMCT_STR2(x) #x
 #define SMCT_STR(x) SMCT_STR2(x)
   return "libsmct_b200 abi " SMCT_STR(SMCT_ABI_VERSION) " | sm_100a | nvcc " SMCT_STR(__CUDACC_VER_MAJOR__) "." SMCT_STR(
-      __CUDACC_VER_MINOR__) " | " __DATE__ " " __TIME__;
+      __CUDACC_VER_MINOR__) " | " __DATE__ " " __TIME__ " | src " SMCT_SOURCE_HASH;
+}
+
+const char* smct_source_hash(void) {
+  static const char tagged[] = "smct-source-hash:" SMCT_SOURCE_HASH;   // the tag lets build.py find the hash in the binary's bytes
+  return tagged + 17;
 }
 
 long long smct_launch_count(int reset) {

@@ -27,6 +27,11 @@ __device__ __forceinline__ float group_sum(float v) {
   return v;
 }
 
+// caller-supplied indices (token ids, class ids, forced ancestor indices) are clamped into range on the device: an
+// out-of-range value can then never touch memory outside the tensor it indexes (the Python binding rejects such
+// inputs with a ValueError before the launch, like TensorFlow's InvalidArgument on CPU)
+__device__ __forceinline__ int clamp_index(int v, int n) { return min(max(v, 0), n - 1); }
+
 // block-wide reductions through a 32-float scratch (all threads get the result)
 __device__ __forceinline__ float block_sum(float v, float* scratch) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
@@ -89,6 +94,17 @@ __device__ __forceinline__ void philox_normal4(uint64_t seed, uint32_t which, ui
                                 (uint32_t)(seed >> 32));
   box_muller(x.x, x.y, n[0], n[1]);
   box_muller(x.z, x.w, n[2], n[3]);
+}
+
+// out-of-line variant for call sites that are unrolled many times (keeps the instruction footprint small: the fused
+// forward is bound by instruction-cache misses when every normal carries its own copy of the generator)
+__device__ __noinline__ float4 philox_normal4_call(uint32_t seed_lo, uint32_t seed_hi, uint32_t which, uint32_t t,
+                                                   uint32_t grp_lo, uint32_t grp_hi) {
+  const u32x4 x = philox4x32(grp_lo, grp_hi, which, t, seed_lo, seed_hi);
+  float4 n;
+  box_muller(x.x, x.y, n.x, n.y);
+  box_muller(x.z, x.w, n.z, n.w);
+  return n;
 }
 
 // one standard normal: element d of particle bp (global particle index) with GD = ceil(D/4)

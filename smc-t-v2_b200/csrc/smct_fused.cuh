@@ -161,7 +161,7 @@ __device__ __forceinline__ void fused_resample_update(FusedCommon& c, FusedResam
     const long long ti = ((long long)t * a.B + b) * P + p;
     int idx;
     if (a.i_forced) {
-      idx = a.i_forced[ti];
+      idx = clamp_index(a.i_forced[ti], P);
     } else {
       const double uu = a.u ? a.u[ti]
                             : philox_uniform(a.seed, (uint32_t)t,

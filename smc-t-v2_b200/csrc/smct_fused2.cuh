@@ -55,7 +55,12 @@ struct Fused2Smem {
   __align__(8) uint64_t mbar_ready, mbar_full[2], mbar_z, mbar_h[2], mbar_r;
   uint32_t tmem_slot;
 };
-static_assert(sizeof(FusedResampleScratch) <= 2 * 2 * tc::B_PART_BYTES, "resample scratch must fit the weight stream buffers");
+struct Fused2Scratch {   // scratch of the draw / genealogy update; lives in the weight stream buffers between timesteps
+  double cdf[FPMAX];                    // fp64 CDF of the draw; afterwards the per-ancestor child counts and their scan (uint32)
+  unsigned short cnt[F2NW][FPMAX];      // children of ancestor position a among the logical ids of segment w
+  unsigned short src[FPMAX], anc[FPMAX], rank[FPMAX];
+};
+static_assert(sizeof(Fused2Scratch) <= 2 * 2 * tc::B_PART_BYTES, "resample scratch must fit the weight stream buffers");
 static_assert(sizeof(Fused2Smem) + 128 <= 113 * 1024, "two CTAs of the fused kernel must fit one SM");
 
 namespace f2 {
@@ -103,7 +108,7 @@ __device__ __forceinline__ void load_a8(const unsigned char* base, int r, int k0
 
 // logsumexp normalise, TF-CPU categorical draw (fp64 sequential CDF in logical particle order), genealogy update.
 // Same semantics as fused_resample_update (smct_fused.cuh); the position table lives in global memory (pos_out).
-__device__ __forceinline__ void resample_update(Fused2Smem& sm, FusedResampleScratch& rx, const FusedArgs& a, int b, int t,
+__device__ __forceinline__ void resample_update(Fused2Smem& sm, Fused2Scratch& rx, const FusedArgs& a, int b, int t,
                                                 unsigned short*& Acur, unsigned short*& Anxt, int& cur_is_A0) {
   const int tid = threadIdx.x;
   const int P = a.P, S = a.S, Sa = a.Sa;
@@ -140,7 +145,7 @@ __device__ __forceinline__ void resample_update(Fused2Smem& sm, FusedResampleScr
     const long long ti = ((long long)t * a.B + b) * P + p;
     int idx;
     if (a.i_forced) {
-      idx = min(max(a.i_forced[ti], 0), P - 1);
+      idx = clamp_index(a.i_forced[ti], P);
     } else {
       const double uu = a.u ? a.u[ti]
                             : philox_uniform(a.seed, (uint32_t)t,
@@ -160,43 +165,93 @@ __device__ __forceinline__ void resample_update(Fused2Smem& sm, FusedResampleScr
 
   const bool resample_now = (a.len_resampling < 0) || (t < a.len_resampling);
   if (resample_now) {
-    int np2 = 1;
-    while (np2 < P) np2 <<= 1;
-    for (int p = tid; p < np2; p += F2NT)
-      rx.keys[p] = (p < P) ? (((unsigned int)pos[rx.anc[p]] << 16) | (unsigned int)p) : 0xFFFFFFFFu;
+    // New genealogy order = the new particles sorted by (position of the ancestor, logical id): a stable counting sort.
+    // The 8 warps own 8 contiguous segments of logical ids; cnt[w][a] counts the children of ancestor position a in
+    // segment w, so  position(p) = (children of smaller a) + (children of a in earlier segments) + (rank of p among the
+    // children of a in its own segment).  Deterministic (no atomics): inside a warp, __match_any groups equal keys.
+    unsigned short* cnt = &rx.cnt[0][0];                                       // [F2NW][P]
+    unsigned short* rank = rx.rank;                                            // rank of p among the children of a in its segment
+    const int lane = tid & 31, wid = tid >> 5;
+    for (int i = tid; i < F2NW * P; i += F2NT) cnt[i] = 0;
     __syncthreads();
-    for (int k = 2; k <= np2; k <<= 1) {
-      for (int j = k >> 1; j > 0; j >>= 1) {
-        for (int i = tid; i < np2; i += F2NT) {
-          const int ixj = i ^ j;
-          if (ixj > i) {
-            const unsigned int kx = rx.keys[i], yv = rx.keys[ixj];
-            const bool up = ((i & k) == 0);
-            if ((kx > yv) == up) { rx.keys[i] = yv; rx.keys[ixj] = kx; }
-          }
-        }
-        __syncthreads();
+    const int seg = (P + F2NW - 1) / F2NW;
+    const int p_lo = wid * seg, p_hi = min(P, p_lo + seg);
+    for (int p0 = p_lo; p0 < p_hi; p0 += 32) {
+      const int p = p0 + lane;
+      const bool on = p < p_hi;
+      const int akey = on ? (int)pos[rx.anc[p]] : (0x10000 + lane);           // inactive lanes: unique keys
+      const unsigned m = __match_any_sync(SMCT_FULL_MASK, akey);
+      if (on) {
+        const int before = cnt[wid * P + akey];
+        rank[p] = (unsigned short)(before + __popc(m & ((1u << lane) - 1u)));
+        rx.anc[p] = (unsigned short)akey;                                      // from here on: the ancestor's POSITION
       }
-    }
-    for (int qn = tid; qn < P; qn += F2NT) {
-      const unsigned int key = rx.keys[qn];
-      rx.src[qn] = (unsigned short)(key >> 16);
-      sm.Lq[qn] = (unsigned short)(key & 0xFFFFu);
-      pos[key & 0xFFFFu] = (unsigned short)qn;
+      __syncwarp();
+      if (on && (m & ((1u << lane) - 1u)) == 0u) cnt[wid * P + akey] = (unsigned short)(cnt[wid * P + akey] + __popc(m));
+      __syncwarp();
     }
     __syncthreads();
+    // per ancestor position: exclusive prefix over the segments and the total (the CDF is dead: its bytes hold the totals)
+    unsigned int* tot = reinterpret_cast<unsigned int*>(rx.cdf);                // [P] totals, then their exclusive scan
+    for (int aa = tid; aa < P; aa += F2NT) {
+      unsigned int run = 0;
+#pragma unroll
+      for (int w = 0; w < F2NW; ++w) { const unsigned int c = cnt[w * P + aa]; cnt[w * P + aa] = (unsigned short)run; run += c; }
+      tot[aa] = run;
+    }
+    __syncthreads();
+    {  // exclusive scan of tot[0..P): each thread owns 4 consecutive entries (P <= 1024 = 4 * F2NT)
+      unsigned int v[4], sum = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { const int aa = 4 * tid + k; v[k] = aa < P ? tot[aa] : 0u; sum += v[k]; }
+      unsigned int inc = sum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const unsigned int n = __shfl_up_sync(SMCT_FULL_MASK, inc, o); if (lane >= o) inc += n; }
+      unsigned int* wsum = reinterpret_cast<unsigned int*>(red);
+      if (lane == 31) wsum[wid] = inc;
+      __syncthreads();
+      unsigned int base = 0;
+      for (int w = 0; w < wid; ++w) base += wsum[w];
+      unsigned int run = base + inc - sum;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { const int aa = 4 * tid + k; if (aa < P) tot[aa] = run; run += v[k]; }
+    }
+    __syncthreads();
+    for (int p = tid; p < P; p += F2NT) {
+      const int akey = rx.anc[p];
+      const int qn = (int)tot[akey] + (int)cnt[(p / seg) * P + akey] + (int)rank[p];
+      sm.Lq[qn] = (unsigned short)p;
+      pos[p] = (unsigned short)qn;
+      rx.src[qn] = (unsigned short)akey;   // position of the ancestor of the particle now at qn
+    }
+    __syncthreads();
+    // ancestry rows: Anxt[q'][0..t) = Acur[src[q']][0..t) ; Anxt[q'][t] = src[q']   (8 slots = one uint4; 4 copies in flight)
     const int nch = (t >> 3) + 1;
-    for (int i = tid; i < P * nch; i += F2NT) {
-      const int qn = i / nch, ch = i - qn * nch;
-      const int sq = rx.src[qn];
-      uint4 v = *reinterpret_cast<const uint4*>(Acur + (long long)sq * Sa + 8 * ch);
-      if ((t >> 3) == ch) {
-        const int e = t & 7;
-        unsigned int wv = (e >> 1) == 0 ? v.x : ((e >> 1) == 1 ? v.y : ((e >> 1) == 2 ? v.z : v.w));
-        wv = (e & 1) ? ((wv & 0x0000FFFFu) | ((unsigned int)sq << 16)) : ((wv & 0xFFFF0000u) | (unsigned int)sq);
-        if ((e >> 1) == 0) v.x = wv; else if ((e >> 1) == 1) v.y = wv; else if ((e >> 1) == 2) v.z = wv; else v.w = wv;
+    const int total = P * nch;
+    for (int i0 = tid; i0 < total; i0 += 4 * F2NT) {
+      uint4 v[4];
+      int sqv[4], qv[4], cv[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int i = i0 + k * F2NT;
+        const bool ok = i < total;
+        const int qn = ok ? i / nch : 0;
+        qv[k] = qn; cv[k] = ok ? i - qn * nch : 0; sqv[k] = rx.src[qn];
+        v[k] = *reinterpret_cast<const uint4*>(Acur + (long long)sqv[k] * Sa + 8 * cv[k]);
       }
-      *reinterpret_cast<uint4*>(Anxt + (long long)qn * Sa + 8 * ch) = v;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (i0 + k * F2NT >= total) continue;
+        uint4 x = v[k];
+        if ((t >> 3) == cv[k]) {   // patch slot t (little-endian: element e is half (e&1) of word (e>>1))
+          const int e = t & 7;
+          const unsigned int sq = (unsigned int)sqv[k];
+          unsigned int wv = (e >> 1) == 0 ? x.x : ((e >> 1) == 1 ? x.y : ((e >> 1) == 2 ? x.z : x.w));
+          wv = (e & 1) ? ((wv & 0x0000FFFFu) | (sq << 16)) : ((wv & 0xFFFF0000u) | sq);
+          if ((e >> 1) == 0) x.x = wv; else if ((e >> 1) == 1) x.y = wv; else if ((e >> 1) == 2) x.z = wv; else x.w = wv;
+        }
+        *reinterpret_cast<uint4*>(Anxt + (long long)qv[k] * Sa + 8 * cv[k]) = x;
+      }
     }
     unsigned short* tmp = Acur; Acur = Anxt; Anxt = tmp;
     cur_is_A0 ^= 1;
@@ -207,6 +262,10 @@ __device__ __forceinline__ void resample_update(Fused2Smem& sm, FusedResampleScr
 
 }  // namespace f2
 
+// INJECT: eps are injected (tests) instead of drawn; MULTI: per-dimension log-variances; CHECKOUT: noise_z = z - z_
+// (self_attention_SMC.py:190).  Compile-time variants keep the instruction footprint of the hot loop small (the kernel
+// is sensitive to instruction-cache misses: its warps run different phases at the same time).
+template <bool INJECT, bool MULTI, bool CHECKOUT>
 __global__ void __launch_bounds__(F2NT, 2) fused2_forward_kernel(const FusedArgs a) {
   extern __shared__ unsigned char smem_raw_f2[];
   Fused2Smem& sm = *reinterpret_cast<Fused2Smem*>(smem_raw_f2 + ((128u - (tc::smem_u32(smem_raw_f2) & 127u)) & 127u));
@@ -230,7 +289,7 @@ __global__ void __launch_bounds__(F2NT, 2) fused2_forward_kernel(const FusedArgs
   const uint32_t tlane = ((uint32_t)(equad * 32)) << 16;
   const uint32_t idesc = tc::make_idesc(128, 64);
   const int nch = a.dff / FD;                     // FFN chunks of 64 hidden units (1..4)
-  const bool multi = a.logvar_dim > 1;
+  constexpr bool multi = MULTI;
   const unsigned char* const hdr_g = a.wtc + (size_t)(1 + 2 * nch) * 2 * tc::B_PART_BYTES;
   const float* const sigtab = reinterpret_cast<const float*>(hdr_g + 256);   // [8][64]: std k,q,v,z ; 1/var k,q,v,z
   double dloss_q = 0.0, dloss_z = 0.0;            // thread 0 only
@@ -263,7 +322,7 @@ __global__ void __launch_bounds__(F2NT, 2) fused2_forward_kernel(const FusedArgs
   tc::fence_after_sync();
   const uint32_t tmem = sm.tmem_slot;
   const uint32_t tD_z = tmem, tD_h0 = tmem + 64, tD_r = tmem + 192;   // z | h even chunk | h odd chunk | r
-  FusedResampleScratch& rsx = *reinterpret_cast<FusedResampleScratch*>(&sm.W[0][0]);
+  Fused2Scratch& rsx = *reinterpret_cast<Fused2Scratch*>(&sm.W[0][0]);
   const unsigned char* const wblk = a.wtc;
   constexpr uint32_t WB = 2 * tc::B_PART_BYTES;   // bytes of one weight block (h and m parts)
   const float s_q = sm.hdr.s_q, s_k = sm.hdr.s_k, s_v = sm.hdr.s_v;
@@ -290,8 +349,8 @@ __global__ void __launch_bounds__(F2NT, 2) fused2_forward_kernel(const FusedArgs
       const bool warp_act = 16 * wid < np;
       if (warp_act) {
         uint4* Qf = reinterpret_cast<uint4*>(sm.Ob) + wid * 256;   // this warp's Q fragments
-        float qsA[16];
-#pragma unroll
+        // rolled loops (two particles x four groups of 4 dims): one copy of the generator in the instruction stream
+#pragma unroll 1
         for (int pp = 0; pp < 2; ++pp) {
           const int pl = 16 * wid + r8 + 8 * pp;       // particle of the tile
           const bool act = pl < np;
@@ -300,15 +359,16 @@ __global__ void __launch_bounds__(F2NT, 2) fused2_forward_kernel(const FusedArgs
           const unsigned long long gbp = (unsigned long long)(a.b_global0 + b) * (unsigned long long)P + L;
           const long long lrow = ((bP + L) * S + t) * FD;
           const uint32_t prow = (uint32_t)(t * P + qc) * FD;
-          float ko[16], vo[16], qs[16];
-#pragma unroll
+          unsigned char* const ksr = Ksb + ((size_t)(t * P + qc) << 8);   // fp16 (h,m) split copies of the new rows in the
+          unsigned char* const vsr = Vsb + ((size_t)(t * P + qc) << 8);   // MMA operand order (smct_fused_attn.cuh)
+#pragma unroll 1
           for (int i = 0; i < 4; ++i) {
             const int cg = 4 * c4 + i, d0 = 4 * cg;      // this lane owns dims [16 c4, 16 c4 + 16)
             const float4 q_0 = *reinterpret_cast<const float4*>(&sm.rowbuf[1][d0]);
             const float4 k_0 = *reinterpret_cast<const float4*>(&sm.rowbuf[2][d0]);
             const float4 v_0 = *reinterpret_cast<const float4*>(&sm.rowbuf[3][d0]);
             float ek[4], eq[4], ev[4];
-            if (a.eps) {
+            if (INJECT) {
               const long long BPD = (long long)a.B * P * FD;
               const long long e0 = ((long long)t * a.B + b) * P * FD + (long long)L * FD + d0;
               const float4 t0 = *reinterpret_cast<const float4*>(a.eps + (0LL * S) * BPD + e0);
@@ -332,55 +392,48 @@ __global__ void __launch_bounds__(F2NT, 2) fused2_forward_kernel(const FusedArgs
 #pragma unroll
               for (int e = 0; e < 4; ++e) { sdk[e] = sm.sig[0]; sdq[e] = sm.sig[1]; sdv[e] = sm.sig[2]; ivq[e] = sm.sig[4]; }
             }
-            float qo[4], nq[4];
+            float ko[4], vo[4], qs[4], nq[4], xk[4], xv[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              ko[4 * i + e] = __fadd_rn(kin[e], __fmul_rn(sdk[e], ek[e]));
-              qo[e] = __fadd_rn(qin[e], __fmul_rn(sdq[e], eq[e]));
-              vo[4 * i + e] = __fadd_rn(vin[e], __fmul_rn(sdv[e], ev[e]));
-              nq[e] = qo[e] - qin[e];
+              ko[e] = __fadd_rn(kin[e], __fmul_rn(sdk[e], ek[e]));
+              const float qo = __fadd_rn(qin[e], __fmul_rn(sdq[e], eq[e]));
+              vo[e] = __fadd_rn(vin[e], __fmul_rn(sdv[e], ev[e]));
+              nq[e] = qo - qin[e];
               loss_q = act ? fmaf(nq[e] * nq[e], ivq[e], loss_q) : loss_q;
-              qs[4 * i + e] = attn::sat16(qo[e] * s_q);   // scaled by log2(e)/sqrt(d_k) (scores in the log2 domain) and the fp16 scale
+              qs[e] = attn::sat16(qo * s_q);   // scaled by log2(e)/sqrt(d_k) (scores in the log2 domain) and the fp16 scale
+              xk[e] = attn::sat16(ko[e] * s_k);
+              xv[e] = attn::sat16(vo[e] * s_v);
             }
-            if (act) {   // fp32 rows: read again only by the final pass
-              __stcs(reinterpret_cast<float4*>(Kb + prow + d0), make_float4(ko[4 * i], ko[4 * i + 1], ko[4 * i + 2], ko[4 * i + 3]));
-              __stcs(reinterpret_cast<float4*>(Vb + prow + d0), make_float4(vo[4 * i], vo[4 * i + 1], vo[4 * i + 2], vo[4 * i + 3]));
+            if (act) {
+              // fp32 rows: read again only by the final pass
+              __stcs(reinterpret_cast<float4*>(Kb + prow + d0), make_float4(ko[0], ko[1], ko[2], ko[3]));
+              __stcs(reinterpret_cast<float4*>(Vb + prow + d0), make_float4(vo[0], vo[1], vo[2], vo[3]));
               if (a.noise_q) __stcs(reinterpret_cast<float4*>(a.noise_q + lrow + d0), make_float4(nq[0], nq[1], nq[2], nq[3]));
+              // split rows: these 4 dims are one half (8 bytes) of the 16-byte unit of dims 16 c4 + 8 (i>>1) .. + 7
+              uint2 h, m;
+              attn::split2(xk[0], xk[1], h.x, m.x);
+              attn::split2(xk[2], xk[3], h.y, m.y);
+              *reinterpret_cast<uint2*>(ksr + 16 * ((i >> 1) * 4 + c4) + 8 * (i & 1)) = h;
+              *reinterpret_cast<uint2*>(ksr + 16 * (8 + (i >> 1) * 4 + c4) + 8 * (i & 1)) = m;
+              attn::split2(xv[0], xv[1], h.x, m.x);
+              attn::split2(xv[2], xv[3], h.y, m.y);
+              *reinterpret_cast<uint2*>(vsr + 32 * c4 + 8 * i) = h;
+              *reinterpret_cast<uint2*>(vsr + 128 + 32 * c4 + 8 * i) = m;
             }
-          }
-          if (act) {   // fp16 (h,m) split copies of the new rows in the MMA operand order (smct_fused_attn.cuh)
-            unsigned char* ksr = Ksb + ((size_t)(t * P + qc) << 8);
-            unsigned char* vsr = Vsb + ((size_t)(t * P + qc) << 8);
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-              float x[8];
-              uint4 h, m;
-#pragma unroll
-              for (int e = 0; e < 8; ++e) x[e] = ko[8 * half + e] * s_k;
-              attn::split8(x, h, m);
-              *reinterpret_cast<uint4*>(ksr + 16 * (half * 4 + c4)) = h;
-              *reinterpret_cast<uint4*>(ksr + 16 * (8 + half * 4 + c4)) = m;
-#pragma unroll
-              for (int e = 0; e < 8; ++e) x[e] = vo[8 * half + e] * s_v;
-              attn::split8(x, h, m);
-              *reinterpret_cast<uint4*>(vsr + 32 * c4 + 16 * half) = h;
-              *reinterpret_cast<uint4*>(vsr + 128 + 32 * c4 + 16 * half) = m;
-            }
-          }
-          if (pp == 0) {
-#pragma unroll
-            for (int e = 0; e < 16; ++e) qsA[e] = qs[e];
-          } else {
-            // Q fragments of the warp's 16 x 64 tile (rows r8 and r8 + 8): k-step j covers dims 16 c4 + 4 j .. + 3 of this lane
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            // Q fragments of the warp's 16 x 64 tile (rows r8 and r8 + 8): k-step i covers dims 16 c4 + 4 i .. + 3 of this
+            // lane.  The first particle parks its four values in the m slot; the second one builds both units.
+            float4* const park = reinterpret_cast<float4*>(&Qf[(4 + i) * 32 + lane]);
+            if (pp == 0) {
+              *park = make_float4(qs[0], qs[1], qs[2], qs[3]);
+            } else {
+              const float4 qa = *park;
               uint4 qh, qm;
-              attn::split2(qsA[4 * j], qsA[4 * j + 1], qh.x, qm.x);
-              attn::split2(qs[4 * j], qs[4 * j + 1], qh.y, qm.y);
-              attn::split2(qsA[4 * j + 2], qsA[4 * j + 3], qh.z, qm.z);
-              attn::split2(qs[4 * j + 2], qs[4 * j + 3], qh.w, qm.w);
-              Qf[j * 32 + lane] = qh;
-              Qf[(4 + j) * 32 + lane] = qm;
+              attn::split2(qa.x, qa.y, qh.x, qm.x);
+              attn::split2(qs[0], qs[1], qh.y, qm.y);
+              attn::split2(qa.z, qa.w, qh.z, qm.z);
+              attn::split2(qs[2], qs[3], qh.w, qm.w);
+              Qf[i * 32 + lane] = qh;
+              Qf[(4 + i) * 32 + lane] = qm;
             }
           }
         }
@@ -514,12 +567,14 @@ __global__ void __launch_bounds__(F2NT, 2) fused2_forward_kernel(const FusedArgs
 #pragma unroll
         for (int gq = 0; gq < 8; ++gq) {
           const int n = n0 + 4 * gq;
-          if (a.eps) {
+          if (INJECT) {
             const float4 t3 = *reinterpret_cast<const float4*>(a.eps + (3LL * S) * ((long long)a.B * P * FD) +
                                                                ((long long)t * a.B + b) * P * FD + (long long)eL * FD + n);
             ezv[4 * gq] = t3.x; ezv[4 * gq + 1] = t3.y; ezv[4 * gq + 2] = t3.z; ezv[4 * gq + 3] = t3.w;
           } else {
-            philox_normal4(a.seed, 3u, (uint32_t)t, gbp * 16ull + (n >> 2), &ezv[4 * gq]);
+            const unsigned long long grp = gbp * 16ull + (n >> 2);
+            const float4 nz = philox_normal4_call((uint32_t)a.seed, (uint32_t)(a.seed >> 32), 3u, (uint32_t)t, (uint32_t)grp, (uint32_t)(grp >> 32));
+            ezv[4 * gq] = nz.x; ezv[4 * gq + 1] = nz.y; ezv[4 * gq + 2] = nz.z; ezv[4 * gq + 3] = nz.w;
           }
         }
       }
@@ -551,7 +606,7 @@ __global__ void __launch_bounds__(F2NT, 2) fused2_forward_kernel(const FusedArgs
         for (int gq = 0; gq < 8; ++gq) {
           const int n = n0 + 4 * gq;
           float z_[4] = {0.f, 0.f, 0.f, 0.f};
-          if (a.noise_z_mode == SMCT_NOISE_Z_CHECKOUT) {   // z_ back from its operand rows (22 bits)
+          if (CHECKOUT) {   // z_ back from its operand rows (22 bits)
             const uint32_t off = tc::operand_offset(er, n);
             const uint2 h = *reinterpret_cast<const uint2*>(sm.ZH + off), m = *reinterpret_cast<const uint2*>(sm.ZH + tc::A_PART_BYTES + off);
             const float2 h0 = __half22float2(*reinterpret_cast<const __half2*>(&h.x)), h1 = __half22float2(*reinterpret_cast<const __half2*>(&h.y));
@@ -569,7 +624,7 @@ __global__ void __launch_bounds__(F2NT, 2) fused2_forward_kernel(const FusedArgs
           for (int e = 0; e < 4; ++e) {
             const float zp = fmaf(val[4 * gq + e], zscale, cbz[e]);   // scale is a power of two: exact
             const float z = __fadd_rn(zp, __fmul_rn(csd[e], ezv[4 * gq + e]));
-            nzv[e] = (a.noise_z_mode == SMCT_NOISE_Z_CHECKOUT) ? (z - z_[e]) : (z - zp);
+            nzv[e] = CHECKOUT ? (z - z_[e]) : (z - zp);
             loss_z = eact ? fmaf(nzv[e] * nzv[e], civ[e], loss_z) : loss_z;
             val[4 * gq + e] = z + cx[e];
             s1 += val[4 * gq + e];
@@ -694,43 +749,40 @@ __global__ void __launch_bounds__(F2NT, 2) fused2_forward_kernel(const FusedArgs
         const float var = ((qA + qB) + 16.0f * dm * dm) * (1.0f / FD);
         const float rstd = 1.0f / sqrtf(var + a.ln_eps);
         float* rrow = Rb + (uint32_t)(t * P + (eact ? q0 + er : 0)) * FD;
-        float part[F2FY];
-#pragma unroll
-        for (int f = 0; f < F2FY; ++f) part[f] = 0.f;
 #pragma unroll
         for (int gq = 0; gq < 8; ++gq) {
           const int n = n0 + 4 * gq;
-          float r4[4], cg[4], cb[4];
+          float cg[4], cb[4];
           ld4(&sm.ln2g[n], cg); ld4(&sm.ln2b[n], cb);
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const float inv = rstd * cg[e];
-            r4[e] = val[4 * gq + e] * inv + (cb[e] - mean * inv);
+            val[4 * gq + e] = val[4 * gq + e] * inv + (cb[e] - mean * inv);
           }
-          if (eact) __stcs(reinterpret_cast<float4*>(rrow + n), make_float4(r4[0], r4[1], r4[2], r4[3]));   // read again only by the final pass
-#pragma unroll
-          for (int f = 0; f < F2FY; ++f) {
-            if (f < Fy) {
-#pragma unroll
-              for (int e = 0; e < 4; ++e) part[f] = fmaf(r4[e], sm.Wo[(n + e) * Fy + f], part[f]);
-            }
-          }
+          if (eact)   // read again only by the final pass
+            __stcs(reinterpret_cast<float4*>(rrow + n), make_float4(val[4 * gq], val[4 * gq + 1], val[4 * gq + 2], val[4 * gq + 3]));
         }
-        // the upper column half hands its partial dot products to the lower half (slot [0][er]: its own read of it is done)
-        if (ehalf == 1) sm.xch[0][er] = make_float4(part[0], part[1], part[2], part[3]);
+        // output layer: each column half forms its partial dot products and parks them in the exchange slot it has just
+        // read (xch[other half][er]: nobody else reads that slot any more); the lower half then adds the two in a fixed order
+        float* const park = reinterpret_cast<float*>(&sm.xch[ehalf ^ 1][er]);
+#pragma unroll 1
+        for (int f = 0; f < Fy; ++f) {
+          float acc = 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc = fmaf(val[j], sm.Wo[(n0 + j) * Fy + f], acc);
+          park[f] = acc;
+        }
         f2::pair_sync(equad);
         if (ehalf == 0) {
-          const float4 o4 = sm.xch[0][er];
-          const float other[4] = {o4.x, o4.y, o4.z, o4.w};
+          const float* const lo = reinterpret_cast<const float*>(&sm.xch[1][er]);   // own partials (columns 0..31)
+          const float* const hi = reinterpret_cast<const float*>(&sm.xch[0][er]);   // the upper half's (columns 32..63)
           float sq = 0.f;
-#pragma unroll
-          for (int f = 0; f < F2FY; ++f) {
-            if (f < Fy) {
-              const float pr = part[f] + other[f];
-              if (eact && a.pred) a.pred[((bP + eL) * S + t) * Fy + f] = pr;
-              const float diff = a.y[((long long)b * S + t) * Fy + f] - pr;
-              sq = fmaf(diff, diff, sq);
-            }
+#pragma unroll 1
+          for (int f = 0; f < Fy; ++f) {
+            const float pr = lo[f] + hi[f];
+            if (eact && a.pred) a.pred[((bP + eL) * S + t) * Fy + f] = pr;
+            const float diff = a.y[((long long)b * S + t) * Fy + f] - pr;
+            sq = fmaf(diff, diff, sq);
           }
           if (eact) sm.lw[eL] = (-0.5f * sq) / a.sigma_obs;
         }
@@ -740,7 +792,7 @@ __global__ void __launch_bounds__(F2NT, 2) fused2_forward_kernel(const FusedArgs
 
     // =========================== end of the timestep: loss partials, draw, genealogy update ===========================
     __syncthreads();   // all tiles done: lw complete, operand / weight buffers idle
-    FusedResampleScratch& rx = rsx;
+    Fused2Scratch& rx = rsx;
     if (a.loss_sums) {
       float* red = reinterpret_cast<float*>(&sm.xch[0][0]);
       const float sq = warp_sum(loss_q), sz = warp_sum(loss_z);

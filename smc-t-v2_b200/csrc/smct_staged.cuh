@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(128) rows_kernel(const RowsArgs a) {
       if (a.input_mode == SMCT_INPUT_ENCODED) {
         x = ((const float*)a.x_in)[row * D + d];
       } else if (a.input_mode == SMCT_INPUT_EMBEDDING) {
-        const int tok = ((const int*)a.x_in)[row];
+        const int tok = clamp_index(((const int*)a.x_in)[row], a.Fx);
         x = a.W_in[(long long)tok * D + d] * a.sqrtD;
       } else {
         const float* xr = (const float*)a.x_in + row * a.Fx;
@@ -531,7 +531,7 @@ __device__ __forceinline__ void resample_seq(const ResampleArgs& a, const int b,
     const long long bp = (long long)b * P + p;
     int idx;
     if (a.i_forced) {
-      idx = a.i_forced[bp];
+      idx = clamp_index(a.i_forced[bp], P);
     } else {
       const double uu = a.u ? a.u[bp]
                             : philox_uniform(a.seed, (uint32_t)a.t_rng,
@@ -580,7 +580,7 @@ __global__ void __launch_bounds__(256) gather_kernel(const GatherArgs a) {
   const long long per = vec ? (n >> 2) : n;                       // copy units per row
   if (a.ppc == 1) {   // long rows: one row per CTA (and grid.y slices of it), no per-unit index arithmetic
     const int b = (int)(bp0 / a.P);
-    const float* __restrict__ src = sbase + ((long long)b * a.P + a.idx[bp0]) * a.row_elems;
+    const float* __restrict__ src = sbase + ((long long)b * a.P + clamp_index(a.idx[bp0], a.P)) * a.row_elems;
     float* __restrict__ dst = dbase + bp0 * a.row_elems;
     if (vec) {
       for (long long i = (long long)blockIdx.y * blockDim.x + threadIdx.x; i < per; i += (long long)gridDim.y * blockDim.x)
@@ -595,7 +595,7 @@ __global__ void __launch_bounds__(256) gather_kernel(const GatherArgs a) {
   for (long long i = (long long)blockIdx.y * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.y * blockDim.x) {
     const long long bp = bp0 + i / per, e = i % per;
     const int b = (int)(bp / a.P);
-    const long long so = ((long long)b * a.P + a.idx[bp]) * a.row_elems, dofs = bp * a.row_elems;
+    const long long so = ((long long)b * a.P + clamp_index(a.idx[bp], a.P)) * a.row_elems, dofs = bp * a.row_elems;
     if (vec) reinterpret_cast<float4*>(dbase + dofs)[e] = reinterpret_cast<const float4*>(sbase + so)[e];
     else dbase[dofs + e] = sbase[so + e];
   }
@@ -795,7 +795,7 @@ __global__ void logweights_kernel(int B, int P, int Fy, int mode, float sigma_ob
       for (int f = 0; f < Fy; ++f) mx = fmaxf(mx, pr[f]);
       float se = 0.f;
       for (int f = 0; f < Fy; ++f) se += expf(pr[f] - mx);
-      logw[bp] = expf(pr[((const int*)y)[b]] - mx) / se;
+      logw[bp] = expf(pr[clamp_index(((const int*)y)[b], Fy)] - mx) / se;
     }
   }
 }
@@ -820,7 +820,7 @@ __global__ void __launch_bounds__(256) classic_loss_kernel(int B, int P, int S, 
       for (int f = 0; f < Fy; ++f) mx = fmaxf(mx, pr[f]);
       float se = 0.f;
       for (int f = 0; f < Fy; ++f) se += expf(pr[f] - mx);
-      acc += (double)(mx + logf(se) - pr[((const int*)y)[(long long)b * S + s]]);
+      acc += (double)(mx + logf(se) - pr[clamp_index(((const int*)y)[(long long)b * S + s], Fy)]);
     }
   }
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(SMCT_FULL_MASK, acc, o);

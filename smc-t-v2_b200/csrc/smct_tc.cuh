@@ -111,6 +111,7 @@ __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier
 __device__ __forceinline__ void mbar_wait(uint64_t* mbar, uint32_t parity) {
   const uint32_t addr = smem_u32(mbar);
   uint32_t done = 0;
+#pragma unroll 1   // (the compiler otherwise unrolls the spin loop 32 times at every wait site)
   for (uint32_t spin = 0; spin < (1u << 22); ++spin) {
     asm volatile(
         "{\n\t"

@@ -31,10 +31,12 @@ def inference_onestep(smc_transformer, inputs, targets, save_path, past_len=40):
     return preds_future, mean_preds
 
 
-def inference_multistep(smc_transformer, inputs, targets, past_len=40, future_len=20, seed=0):
+def inference_multistep(smc_transformer, inputs, targets, past_len=40, future_len=20, seed=0, eps=None, u=None,
+                        obs_noise=None):
     """Multi-step forecast for the regression SMC-T.  inputs/targets (B,1,past_len,F) observed past (F_x == F_y).
     Returns (preds_future (B,P,future_len,F_y), mean over particles (B,future_len,F_y)).  Each future step feeds
-    x_{t+1}[p] = pred_t[p] + sqrt(Sigma_obs) * N(0,1) back as a per-particle input; resampling stops at past_len."""
+    x_{t+1}[p] = pred_t[p] + sqrt(Sigma_obs) * N(0,1) back as a per-particle input; resampling stops at past_len.
+    Tests inject the draws: eps (4,S,B,P,D), u (S,B,P), obs_noise (S,B,P,F_y) with S = past_len + future_len."""
     m = smc_transformer
     c = m.cell
     dev = _device()
@@ -61,18 +63,22 @@ def inference_multistep(smc_transformer, inputs, targets, past_len=40, future_le
     preds = []
     gen = torch.Generator(device=dev).manual_seed(int(seed))
     x_next = None
+    cvt = lambda a, dt: None if a is None else torch.as_tensor(np.asarray(a), device=dev).to(dt).contiguous()
+    eps, u, obs_noise = cvt(eps, torch.float32), cvt(u, torch.float64), cvt(obs_noise, torch.float32)
     for t in range(S):
+        inj = dict(eps4=None if eps is None else eps[:, t].contiguous(), u=None if u is None else u[t].contiguous())
         if t < past_len:
             st = F.cell_step(shape, params, t, X_past[:, t].contiguous(), targets[:, 0, t].contiguous(), K, V, R,
-                             seed=seed, want_attn=False)
+                             seed=seed, want_attn=False, **inj)
         else:
             encp = F.make_shape(B, 1, P, D, F_x=Fx, F_y=Fy, input_mode="linear", dff=m.dff)     # rows = particles
             X_t = F.encode(encp, params, x_next.contiguous())                                   # (B,P,D)
             dummy_y = torch.zeros((B, Fy), device=dev)
-            st = F.cell_step(shape, params, t, X_t, dummy_y, K, V, R, seed=seed, want_attn=False)
+            st = F.cell_step(shape, params, t, X_t, dummy_y, K, V, R, seed=seed, want_attn=False, **inj)
             preds.append(st["pred"])
         # next input of every particle: its own prediction plus observation noise
-        x_next = st["pred"] + math.sqrt(c.Sigma_obs) * torch.randn(st["pred"].shape, device=dev, generator=gen)
+        n_obs = torch.randn(st["pred"].shape, device=dev, generator=gen) if obs_noise is None else obs_noise[t]
+        x_next = st["pred"] + math.sqrt(c.Sigma_obs) * n_obs
     preds_future = torch.stack(preds, dim=2)                                                     # (B,P,future_len,F_y)
     return preds_future, preds_future.mean(dim=1)
 

@@ -62,6 +62,39 @@ def _ptr(t: Optional[torch.Tensor], dtype=None, name="tensor"):
     return ctypes.c_void_p(t.data_ptr())
 
 
+def _check_index_range(t: Optional[torch.Tensor], n: int, name: str):
+    """Integer inputs that index device memory (token ids, class ids, forced ancestor indices) must lie in [0, n):
+    TensorFlow raises InvalidArgument for them on CPU; the kernels clamp, this raises.  One small reduction + sync,
+    only on the integer-input paths (the regression hot path has none)."""
+    if t is None or t.numel() == 0:
+        return
+    lo, hi = (int(v) for v in torch.aminmax(t))
+    if lo < 0 or hi >= n:
+        raise ValueError("%s has values in [%d, %d], outside [0, %d)" % (name, lo, hi, n))
+
+
+def _check_inputs(shape: SmctShape, x_in, y, i_forced=None):
+    B, S = shape.B, shape.S
+    if shape.input_mode == INPUT["embedding"]:
+        if tuple(x_in.shape) != (B, S):
+            raise ValueError("x_in must have shape (B,S) = %s for token inputs, got %s" % ((B, S), tuple(x_in.shape)))
+        _check_index_range(x_in, shape.F_x, "x_in (token ids)")
+    else:
+        want = (B, S, shape.D if shape.input_mode == INPUT["encoded"] else shape.F_x)
+        if tuple(x_in.shape) != want:
+            raise ValueError("x_in must have shape %s, got %s" % (want, tuple(x_in.shape)))
+    if shape.weights_mode == WEIGHTS["classification"]:
+        if tuple(y.shape) != (B, S):
+            raise ValueError("y must have shape (B,S) = %s for class targets, got %s" % ((B, S), tuple(y.shape)))
+        _check_index_range(y, shape.F_y, "y (class ids)")
+    elif tuple(y.shape) != (B, S, shape.F_y):
+        raise ValueError("y must have shape %s, got %s" % ((B, S, shape.F_y), tuple(y.shape)))
+    if i_forced is not None:
+        if tuple(i_forced.shape) != (S, B, shape.P):
+            raise ValueError("i_forced must have shape (S,B,P) = %s, got %s" % ((S, B, shape.P), tuple(i_forced.shape)))
+        _check_index_range(i_forced, shape.P, "i_forced (ancestor indices)")
+
+
 def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -130,6 +163,7 @@ def forward(shape: SmctShape, params: Dict[str, torch.Tensor], x_in: torch.Tenso
     y_dtype = torch.int32 if shape.weights_mode == WEIGHTS["classification"] else torch.float32
     io.x_in = _ptr(x_in, x_dtype, "x_in")
     io.y = _ptr(y, y_dtype, "y")
+    _check_inputs(shape, x_in, y, i_forced)
     if eps is not None and tuple(eps.shape) != (4, S, B, P, D):
         raise ValueError("eps must have shape (4,S,B,P,D)")
     if u is not None and tuple(u.shape) != (S, B, P):
@@ -338,6 +372,9 @@ def backward(shape: SmctShape, params: Dict[str, torch.Tensor], x_in: torch.Tens
     x_dtype = torch.int32 if shape.input_mode == INPUT["embedding"] else torch.float32
     io.x_in = _ptr(x_in, x_dtype, "x_in")
     io.y = _ptr(y, torch.int32 if shape.weights_mode == WEIGHTS["classification"] else torch.float32, "y")
+    _check_inputs(shape, x_in, y)
+    if tuple(fwd["i_out"].shape) != (shape.S, shape.B, shape.P):
+        raise ValueError("fwd['i_out'] must have shape (S,B,P)")
     io.eps = _ptr(eps, torch.float32, "eps")
     io.seed = int(seed)
     io.K = _ptr(fwd["K"], torch.float32, "K")

@@ -24,3 +24,20 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+def pytest_terminal_summary(terminalreporter, exitstatus, config):
+    """Per-tensor worst parity error of the session (tests/util.py:assert_close): fraction of the tolerance used and
+    |err| / max|ref|."""
+    try:
+        from tests import util
+    except Exception:
+        return
+    if not getattr(util, "PARITY_LOG", None):
+        return
+    tr = terminalreporter
+    tr.write_line("")
+    tr.write_line("parity summary (tolerance |a-b| <= %g*|b| + %g*max|b|): tensor, comparisons, worst err/tol, worst err/max|ref|"
+                  % (util.RTOL, util.RTOL * util.ATOL_FRAC))
+    for k, (r_tol, r_scale, n) in sorted(util.PARITY_LOG.items()):
+        tr.write_line("  [parity] %-16s n=%-5d err/tol=%.3f  err/scale=%.2e" % (k, n, r_tol, r_scale))

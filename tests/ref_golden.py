@@ -11,7 +11,7 @@ GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
 
 
 def ref_files():
-    return sorted(glob.glob(os.path.join(GOLDEN, "ref_*.npz")))
+    return sorted(f for f in glob.glob(os.path.join(GOLDEN, "ref_*.npz")) if not os.path.basename(f).startswith("ref_grad_"))
 
 
 def load(path):

@@ -105,3 +105,11 @@ def test_binding_enums_match_the_header():
         assert table == declared, (prefix, table, declared)
     assert (enums["SMCT_OK"], enums["SMCT_ERR_INVALID"], enums["SMCT_ERR_CUDA"], enums["SMCT_ERR_WORKSPACE"],
             enums["SMCT_ERR_UNSUPPORTED"]) == (_lib.OK, _lib.ERR_INVALID, _lib.ERR_CUDA, _lib.ERR_WORKSPACE, _lib.ERR_UNSUPPORTED)
+
+
+def test_library_matches_the_tree(lib):
+    """Build provenance: the .so carries the hash of the sources it was compiled from, and it is this tree's."""
+    from smct_b200 import _build_mod as B
+    assert lib.smct_source_hash().decode() == B.source_hash() == B.built_hash()
+    assert B.source_hash().encode() in lib.smct_build_info()
+    assert not B.needs_build()

@@ -329,17 +329,22 @@ def test_properties_at_scale(algo):
     assert np.array_equal(dev2["i_out"], dev["i_out"]) and np.array_equal(dev2["K"], dev["K"])
 
 
-def test_fused_and_staged_agree_at_scale():
-    """Same seed, both algorithms, C4 particle count: teacher-force the staged path with the fused path's
-    ancestors so that last-bit differences cannot fork the trajectories; everything must then agree."""
-    cfg = O.Config(B=4, P=1024, S=40, D=64, dff=256)
+@pytest.mark.parametrize("algo", ["fused", "fused_v1"])
+@pytest.mark.parametrize("B,S", [(4, 40), (2, 128)])
+def test_fused_and_staged_agree_at_scale(algo, B, S):
+    """Same seed, both algorithms, C4 particle count — (2, 128) is the benchmark's per-CTA workload (P=1024 AND S=128):
+    teacher-force the staged path with the fused path's ancestors so that last-bit differences cannot fork the
+    trajectories; everything must then agree to the parity bar."""
+    cfg = O.Config(B=B, P=1024, S=S, D=64, dff=256)
     p = O.init_params(cfg, sigma2=0.5)
     x_in, y = O.synthetic_series(cfg.B, cfg.S, 1, alpha=0.9, var=0.3)
-    fu = util.run_device(cfg, p, x_in, y, None, None, seed=11, want=("i_out", "logw", "loss_sums"), algo="fused")
-    st = util.run_device(cfg, p, x_in, y, None, None, seed=11, i_forced=fu["i_out"], want=("i_out", "logw", "loss_sums"),
-                         algo="staged")
-    for k in ("pred", "pred_resampl", "K", "V", "R", "w", "logw"):
-        util.assert_close(k, fu[k], st[k])
+    want = ("i_out", "logw", "loss_sums", "noise_q", "noise_z", "noise_K", "noise_V")
+    fu = util.run_device(cfg, p, x_in, y, None, None, seed=11, want=want, algo=algo)
+    st = util.run_device(cfg, p, x_in, y, None, None, seed=11, i_forced=fu["i_out"], want=want, algo="staged")
+    assert np.array_equal(fu["i_out"], st["i_out"])
+    worst = {k: util.assert_close(k, fu[k], st[k]) for k in ("pred", "pred_resampl", "K", "V", "R", "w", "logw", "noise_q",
+                                                             "noise_z", "noise_K", "noise_V")}
+    print("[parity] %s vs staged, B=%d P=1024 S=%d: max rel err %s" % (algo, B, S, {k: "%.1e" % v for k, v in worst.items()}))
     assert np.allclose(fu["loss_sums"][:5], st["loss_sums"][:5], rtol=2e-4)
 
 

@@ -142,3 +142,37 @@ def test_classification_train_step():
     m.seed = 5
     losses = [float(train_step_SMC_T(inp, tar, m, opt, it=i + 1)[0]) for i in range(6)]
     assert np.all(np.isfinite(losses)) and losses[-1] < losses[0], losses
+
+
+def test_forecast_multistep_matches_oracle_rollout():
+    """inference_multistep (incremental roll-out on the particles' K/V cache, smct_cell_step per future step) against
+    the oracle's restatement of the regression-era forecast (oracle/smct_oracle.py:forecast_multistep; reference
+    src/eval/inference_functions.py:19-39 + the shipped pyc) on injected draws."""
+    from oracle import smct_oracle as O
+    from smct_b200 import utils
+    from smct_b200.eval.inference_functions import inference_multistep
+    from smct_b200.models.SMC_Transformer.SMC_Transformer import SMC_Transformer
+    from tests import util
+    B, P, D, dff, past_len, future_len = 3, 12, 16, 16, 9, 6
+    S = past_len + future_len
+    x, y = utils.synthetic_ar1(B, past_len, 1, alpha=0.8, var=0.5)
+    model = SMC_Transformer(d_model=D, output_size=1, seq_len=S, full_model=True, dff=dff)
+    model.cell.add_SMC_parameters(dict_sigmas=dict(k=0.1, q=0.2, v=0.1, z=0.3), num_particles=P, sigma_obs=0.4)
+    inputs, targets = torch.from_numpy(x).unsqueeze(1), torch.from_numpy(y).unsqueeze(1)
+    rng = np.random.default_rng(5)
+    eps = rng.standard_normal((4, S, B, P, D)).astype(np.float32)
+    u = rng.random((S, B, P))
+    obs = rng.standard_normal((S, B, P, 1)).astype(np.float32)
+    params = {k: v.detach().cpu().numpy() for k, v in model._params("regression", 1).items()}
+    cfg = O.Config(B=B, P=P, S=S, D=D, dff=dff, F_x=1, F_y=1, sigma_obs=0.4, noise_z_mode="pyc", len_resampling=past_len)
+    # screen the uniforms of the observed past against the oracle's own CDFs (free-running protocol L4)
+    for _ in range(50):
+        ref = O.forecast_multistep(cfg, params, x, y, eps, u, obs, past_len, future_len)
+        pf, mean = inference_multistep(model, inputs, targets, past_len=past_len, future_len=future_len, eps=eps, u=u, obs_noise=obs)
+        got = pf.cpu().numpy()
+        if np.allclose(got, ref, rtol=1e-3, atol=1e-3):
+            break
+        u = rng.random((S, B, P))          # a draw sat on a CDF boundary: the trajectories forked; redraw
+    assert got.shape == ref.shape == (B, P, future_len, 1)
+    util.assert_close("forecast preds_future", got, ref)
+    util.assert_close("forecast mean", mean.cpu().numpy(), ref.mean(axis=1))

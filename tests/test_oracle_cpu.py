@@ -182,3 +182,28 @@ def test_oracle_matches_reference_sources(path):
 
 def test_reference_fixtures_exist():
     assert len(ref_golden.ref_files()) >= 5
+
+
+def test_gradient_oracle_matches_reference_tape_gradient():
+    """The autograd restatement (oracle/ref_eager_torch.loss_and_grads) that the backward tests use reproduces
+    tape.gradient(loss, trainable_variables) of the reference's own forward and loss code (tests/golden/ref_grad_*.npz,
+    written over the TF shim by oracle/gen_golden_grads_from_reference.py)."""
+    from oracle import ref_eager_torch as E
+    from tests import ref_grad_golden as RG
+    paths = RG.files()
+    assert len(paths) >= 4
+    for path in paths:
+        g, cfg, p, ref, x_in, y, variant = RG.load(path)
+        ora = O.forward(cfg, p, x_in, y, g["eps"], g["u"])
+        _, grads = E.loss_and_grads(cfg, p, x_in, y, g["eps"], ora["i_t"], variant=variant)
+        RG.compare_grads(path, grads, ref)
+
+
+def test_philox_round_count_matches_the_device_header():
+    import re
+    src = open(os.path.join(os.path.dirname(os.path.dirname(__file__)), "smc-t-v2_b200", "csrc", "smct_common.cuh")).read()
+    assert int(re.search(r"SMCT_PHILOX_ROUNDS\s*=\s*(\d+)", src).group(1)) == PH.ROUNDS
+    # the first ROUNDS rounds of the generator whose 10-round form is pinned by the Random123 vectors above
+    a = PH.philox4x32(1, 2, 3, 4, 5, 6)
+    b = PH.philox4x32(1, 2, 3, 4, 5, 6, rounds=PH.ROUNDS)
+    assert [int(v) for v in a] == [int(v) for v in b] != [int(v) for v in PH.philox4x32_10(1, 2, 3, 4, 5, 6)]

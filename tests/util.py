@@ -13,6 +13,19 @@ RTOL = 1e-4
 ATOL_FRAC = 0.1
 
 
+# worst error per tensor name over the whole session, in units of the tolerance and as |err| / max|ref|
+# (printed by tests/conftest.py:pytest_terminal_summary so that the GPU log shows how much margin the bar has)
+PARITY_LOG = {}
+
+
+def _log_parity(name, err, tol, scale):
+    key = name.split(":")[-1]
+    r_tol = float((err / tol).max()) if err.size else 0.0
+    r_scale = float(err.max() / (scale + 1e-30)) if err.size else 0.0
+    old = PARITY_LOG.get(key, (0.0, 0.0, 0))
+    PARITY_LOG[key] = (max(old[0], r_tol), max(old[1], r_scale), old[2] + 1)
+
+
 def assert_close(name, got, ref, rtol=RTOL, atol_frac=ATOL_FRAC):
     got = np.asarray(got, np.float64)
     ref = np.asarray(ref, np.float64)
@@ -20,6 +33,7 @@ def assert_close(name, got, ref, rtol=RTOL, atol_frac=ATOL_FRAC):
     scale = float(np.abs(ref).max()) if ref.size else 0.0
     tol = rtol * np.abs(ref) + rtol * atol_frac * scale + 1e-30
     err = np.abs(got - ref)
+    _log_parity(name, err, tol, scale)
     bad = err > tol
     if bad.any():
         i = np.unravel_index(np.argmax(err / tol), err.shape)
