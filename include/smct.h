@@ -140,7 +140,8 @@ int smct_forward(const smct_shape *shape, const smct_params *params, const smct_
  * Driven by the OUTPUTS of smct_forward on the same shape/params/inputs: io->K, io->V (final states), io->i_out
  * (ancestor indices), io->loss_sums (for the log-variance gradients), io->x_in, io->y and the same io->eps or
  * io->seed.  inv_n = 1 / (global B*P*S) so that chunks / shards of one optimisation step can be accumulated.
- * Supported: gaussian (MSE) and classification (sparse CE) observation models, 1 head, full model, scalar log-variances,
+ * Supported: gaussian (MSE) and classification (sparse CE) observation models, 1 head, full model, scalar or
+ * per-dimension log-variances (the latter need io->noise_K, noise_q, noise_V, noise_z: the forward's recorded noises),
  * noise_z_mode = SMCT_NOISE_Z_PYC (the checkout quirk noise_z = z - z_ is forward-only: its loss term involves particles
  * outside the final genealogy),
  * d_model <= 128, S*d_model <= 12800.  Gradients are ACCUMULATED into `grads`. */

@@ -157,7 +157,7 @@ def loss_and_grads(cfg, p_np, x_in, y, eps, i_forced, variant="pyc"):
             part = 0.5 * (out[n].square() / torch.exp(tp[lv])).sum(-1)
             if variant == "checkout":
                 D = out[n].shape[-1]
-                part = part + 0.5 * D * math.log(2 * math.pi) + 0.5 * D * tp[lv]
+                part = part + 0.5 * D * math.log(2 * math.pi) + (0.5 * D * tp[lv] if tp[lv].dim() == 0 else 0.5 * tp[lv].sum())
             tot = tot + part.mean()
         if classification:   # compute_classic_loss (SMC_Transformer.py:148-164): sparse CE of the resampled logits
             pr = out["pred_resampl"]

@@ -42,6 +42,7 @@ struct GradLayout {
 
 struct BwdArgs {
   int B, P, S, D, dff, Fy, Fx, attn_window, len_resampling, input_mode, weights_mode;
+  int logvar_dim;                         // 1: scalar log-variances; D: per dimension (noise_dim = "multi")
   float ln_eps, sigma_obs, inv_n, sqrtD;
   long long b_global0;
   unsigned long long seed;
@@ -183,7 +184,10 @@ __global__ void __launch_bounds__(256) bwd_attn_fwd_kernel(const BwdArgs a) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int D = a.D, S = a.S;
   const long long nnodes = a.node_off[a.B * S];
-  const float std_q = expf(0.5f * a.p.logvar_q[0]);
+  const bool multi = a.logvar_dim > 1;
+  float std_q[KD];
+#pragma unroll
+  for (int k = 0; k < KD; ++k) { const int d = lane + 32 * k; std_q[k] = expf(0.5f * a.p.logvar_q[(multi && d < D) ? d : 0]); }
   const float sqrt_d = sqrtf((float)D);
   for (long long u = (long long)blockIdx.x * 8 + wid; u < nnodes; u += (long long)gridDim.x * 8) {
     const int bs = a.node_bs[u];
@@ -195,7 +199,7 @@ __global__ void __launch_bounds__(256) bwd_attn_fwd_kernel(const BwdArgs a) {
 #pragma unroll
     for (int k = 0; k < KD; ++k) {
       const int d = lane + 32 * k;
-      q[k] = (d < D) ? __fadd_rn(a.q_[(long long)bs * D + d], __fmul_rn(std_q, bwd_eps(a, 1, b, s, L, d))) : 0.f;
+      q[k] = (d < D) ? __fadd_rn(a.q_[(long long)bs * D + d], __fmul_rn(std_q[k], bwd_eps(a, 1, b, s, L, d))) : 0.f;
       acc[k] = 0.f;
     }
     const float* Kp = a.K + bp * S * D;
@@ -284,7 +288,8 @@ __global__ void __launch_bounds__(NT) bwd_dense_kernel(const BwdArgs a) {
   const int n_small = 6 * D + dff + D * Fy;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   float* rep = a.rep + (long long)blockIdx.x * a.lay.total;
-  const float std_z = expf(0.5f * a.p.logvar_z[0]);
+  const float std_z0 = expf(0.5f * a.p.logvar_z[0]);
+  const bool multi_z = a.logvar_dim > 1;
   const float c_obs = a.inv_n / a.sigma_obs;
   __shared__ int rbs[PT], rL[PT];
   __shared__ float rm[PT];
@@ -313,6 +318,7 @@ __global__ void __launch_bounds__(NT) bwd_dense_kernel(const BwdArgs a) {
       float u = 0.f;
       if (pl < np) {
         const int bs = rbs[pl];
+        const float std_z = multi_z ? expf(0.5f * a.p.logvar_z[n]) : std_z0;
         const float z = __fadd_rn(v, __fmul_rn(std_z, bwd_eps(a, 3, bs / S, bs % S, rL[pl], n)));
         u = z + a.xln[(long long)bs * D + n];
       }
@@ -497,7 +503,13 @@ __global__ void __launch_bounds__(BWD_ANT) bwd_attn_bwd_kernel(const BwdArgs a) 
   constexpr int NWA = BWD_ANT / 32;
   const int b = blockIdx.x / BWD_G, g = blockIdx.x % BWD_G;
   const float sqrt_d = sqrtf((float)D);
-  const float c_k = expf(-a.p.logvar_k[0]) * a.inv_n, c_v = expf(-a.p.logvar_v[0]) * a.inv_n;
+  float c_k[KD], c_v[KD];   // 1/sigma_k^2, 1/sigma_v^2 (per dimension when logvar_dim = D) times the loss normalisation
+#pragma unroll
+  for (int k = 0; k < KD; ++k) {
+    const int d = lane + 32 * k;
+    const int li = (a.logvar_dim > 1 && d < D) ? d : 0;
+    c_k[k] = expf(-a.p.logvar_k[li]) * a.inv_n; c_v[k] = expf(-a.p.logvar_v[li]) * a.inv_n;
+  }
   const long long u_begin = a.node_off[(long long)b * S], u_end = a.node_off[(long long)(b + 1) * S];
   for (int tbase = 0; tbase < S; tbase += NWA * BWD_TJ) {
     float dk[BWD_TJ][KD], dv[BWD_TJ][KD];
@@ -559,8 +571,8 @@ __global__ void __launch_bounds__(BWD_ANT) bwd_attn_bwd_kernel(const BwdArgs a) 
           for (int k = 0; k < KD; ++k) {
             const int d = lane + 32 * k;
             if (d < D) {
-              const float tk = mult * c_k * (kr[k] - a.kx[(long long)bs * D + d]);
-              const float tv = mult * c_v * (vr[k] - a.vx[(long long)bs * D + d]);
+              const float tk = mult * c_k[k] * (kr[k] - a.kx[(long long)bs * D + d]);
+              const float tv = mult * c_v[k] * (vr[k] - a.vx[(long long)bs * D + d]);
               dk[j][k] += tk; dv[j][k] += tv;
               atomicAdd(a.dkx_sum + (long long)bs * D + d, -tk);
               atomicAdd(a.dvx_sum + (long long)bs * D + d, -tv);
@@ -686,6 +698,7 @@ struct ScatterArgs {
   int D, dff, Fy, win_elems;
   const float* flat;
   const double* loss_sums;   // forward's sums: [0] K, [1] q, [2] V, [3] z
+  int scalar_logvar;         // 1: scalar log-variances (their gradients come from loss_sums here); 0: per dimension
   float inv_n, logdet_term;  // logdet_term = 0.5 * D * (rows of this call) * inv_n for the checkout loss variant, else 0
   smct_grads g;
 };
@@ -702,12 +715,33 @@ __global__ void scatter_grads_kernel(const ScatterArgs a) {
   put(a.g.ln1_g, a.lay.ln1_g, D); put(a.g.ln1_b, a.lay.ln1_b, D); put(a.g.ln2_g, a.lay.ln2_g, D); put(a.g.ln2_b, a.lay.ln2_b, D);
   put(a.g.W1, a.lay.W1, D * dff); put(a.g.b1, a.lay.b1, dff); put(a.g.W2, a.lay.W2, dff * D); put(a.g.b2, a.lay.b2, D);
   put(a.g.Wo, a.lay.Wo, D * a.Fy); put(a.g.W_in, a.lay.W_in, a.win_elems); put(a.g.b_in, a.lay.b_in, D);
-  if (i0 == 0 && a.loss_sums) {
+  if (i0 == 0 && a.loss_sums && a.scalar_logvar) {
     if (a.g.logvar_k) a.g.logvar_k[0] += (float)(-0.5 * a.loss_sums[0] * a.inv_n) + a.logdet_term;
     if (a.g.logvar_q) a.g.logvar_q[0] += (float)(-0.5 * a.loss_sums[1] * a.inv_n) + a.logdet_term;
     if (a.g.logvar_v) a.g.logvar_v[0] += (float)(-0.5 * a.loss_sums[2] * a.inv_n) + a.logdet_term;
     if (a.g.logvar_z) a.g.logvar_z[0] += (float)(-0.5 * a.loss_sums[3] * a.inv_n) + a.logdet_term;
   }
+}
+
+// Per-dimension log-variance gradients (noise_dim = "multi", self_attention_SMC.py:57-61,102-107): the loss term of a
+// recorded noise tensor n (rows, D) is  inv_n * sum_rows 1/2 sum_d n_d^2 exp(-logvar_d)  (+ 1/2 sum_d logvar_d per row in
+// the checkout variant), hence  d/dlogvar_d = -1/2 inv_n exp(-logvar_d) sum_rows n_d^2 + logdet.  One pass over the
+// tensor; fp64 column sums (acc: D doubles, zeroed by the caller).
+__global__ void __launch_bounds__(256) colsumsq_kernel(long long rows, int D, const float* __restrict__ n, double* acc) {
+  const int tid = threadIdx.x;
+  const int per = 256 / D > 0 ? 256 / D : 1;          // rows handled side by side by one block (D <= 256)
+  const int d = tid % D, sub = tid / D;
+  if (sub >= per) return;
+  double sum = 0.0;
+  for (long long r = (long long)blockIdx.x * per + sub; r < rows; r += (long long)gridDim.x * per) {
+    const float v = n[r * D + d];
+    sum += (double)v * (double)v;
+  }
+  atomicAdd(acc + d, sum);
+}
+__global__ void logvar_grad_multi_kernel(int D, const double* acc, const float* logvar, float inv_n, float logdet_per_dim, float* grad) {
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d < D) grad[d] += (float)(-0.5 * acc[d] * (double)expf(-logvar[d]) * (double)inv_n) + logdet_per_dim;
 }
 
 // Adam (tf.keras.optimizers.Adam: m, v moments, bias-corrected step size, epsilon outside the sqrt)

@@ -458,8 +458,8 @@ int check_backward_shape(const smct_shape& s) {
   // noise_z_mode checkout (noise_z = z - z_, self_attention_SMC.py:190) makes the noise_z loss term of EVERY per-step
   // particle depend on the parameters, including particles that do not survive to the final genealogy: that term is
   // outside the path-wise formulation (which sees the final lineages only)
-  if (s.H != 1 || !s.full_model || !s.noise_on || s.logvar_dim != 1 || s.noise_z_mode != SMCT_NOISE_Z_PYC)
-    return fail(SMCT_ERR_UNSUPPORTED, "backward supports: 1 head, full model, noise on, scalar log-variances, noise_z_mode pyc");
+  if (s.H != 1 || !s.full_model || !s.noise_on || s.noise_z_mode != SMCT_NOISE_Z_PYC)
+    return fail(SMCT_ERR_UNSUPPORTED, "backward supports: 1 head, full model, noise on, noise_z_mode pyc");
   if (s.D > 128) return fail(SMCT_ERR_UNSUPPORTED, "backward: d_model %d > 128", s.D);
   if ((long long)s.S * s.D > 12800) return fail(SMCT_ERR_UNSUPPORTED, "backward: S*d_model %lld > 12800", (long long)s.S * s.D);
   if (s.P > 12288) return fail(SMCT_ERR_UNSUPPORTED, "backward: particles %d > 12288", s.P);
@@ -479,6 +479,7 @@ size_t backward_ws(const smct_shape& s) {
   n += 3 * align_up(BPS * s.D * 4) + align_up(BPS * 2 * 4);     // Zm, dZm, Qm, stat
   n += 6 * align_up(BSD * 4);                                   // per-row sums
   n += align_up((size_t)BWD_NREP * l.total * 4) + align_up((size_t)l.total * 4);
+  n += align_up((size_t)4 * 256 * sizeof(double));   // per-dimension noise sums (logvar_dim = D)
   return n + 1024;
 }
 
@@ -769,6 +770,10 @@ int smct_backward(const smct_shape* shape, const smct_params* params, const smct
   if (!io->x_in || !io->y || !io->K || !io->V || !io->i_out)
     return fail(SMCT_ERR_INVALID, "smct_backward needs io->x_in, y, K, V (final states) and i_out from the forward");
   if (!(inv_n > 0.f)) return fail(SMCT_ERR_INVALID, "inv_n must be > 0");
+  const bool multi = s.logvar_dim > 1;
+  if (multi && (grads->logvar_k || grads->logvar_q || grads->logvar_v || grads->logvar_z) &&
+      !(io->noise_K && io->noise_q && io->noise_V && io->noise_z))
+    return fail(SMCT_ERR_INVALID, "per-dimension log-variance gradients need the forward's recorded noises: io->noise_K, noise_q, noise_V, noise_z");
   if (!workspace || workspace_bytes < backward_ws(s)) return fail(SMCT_ERR_WORKSPACE, "workspace %zu < required %zu", workspace_bytes, backward_ws(s));
   cudaStream_t st = (cudaStream_t)stream;
   const int B = s.B, P = s.P, S = s.S, D = s.D;
@@ -789,6 +794,7 @@ int smct_backward(const smct_shape* shape, const smct_params* params, const smct
   float* sums = c.take<float>(6 * BSD);   // contiguous: one memset
   float* rep = c.take<float>((size_t)BWD_NREP * lay.total);
   float* flat = c.take<float>((size_t)lay.total);
+  double* colacc = c.take<double>((size_t)4 * 256);
   // `sums` was carved as one block; re-derive the six (B,S,D) views without alignment gaps
   float* dq_sum = sums; float* dk_sum = sums + BSD; float* dv_sum = sums + 2 * BSD; float* dxln_sum = sums + 3 * BSD;
   float* dkx_sum = sums + 4 * BSD; float* dvx_sum = sums + 5 * BSD;
@@ -831,7 +837,7 @@ int smct_backward(const smct_shape* shape, const smct_params* params, const smct
   smct::BwdArgs a;
   memset(&a, 0, sizeof(a));
   a.B = B; a.P = P; a.S = S; a.D = D; a.dff = s.dff; a.Fy = s.F_y; a.Fx = s.F_x; a.attn_window = s.attn_window;
-  a.len_resampling = s.len_resampling; a.input_mode = s.input_mode; a.weights_mode = s.weights_mode;
+  a.len_resampling = s.len_resampling; a.input_mode = s.input_mode; a.weights_mode = s.weights_mode; a.logvar_dim = s.logvar_dim;
   a.ln_eps = s.ln_eps; a.sigma_obs = s.sigma_obs; a.inv_n = inv_n; a.sqrtD = sqrtf((float)D);
   a.b_global0 = s.b_global0; a.seed = io->seed;
   a.x_in = io->x_in; a.X = X; a.xln = xln; a.q_ = q_; a.kx = kx; a.vx = vx;
@@ -855,8 +861,25 @@ int smct_backward(const smct_shape* shape, const smct_params* params, const smct
   sa.flat = flat; sa.loss_sums = io->loss_sums; sa.inv_n = inv_n;
   sa.logdet_term = (loss_variant == SMCT_LOSS_CHECKOUT) ? 0.5f * D * (float)((double)B * P * S * inv_n) : 0.f;
   sa.g = *grads;
+  sa.scalar_logvar = multi ? 0 : 1;
   smct::scatter_grads_kernel<<<64, 256, 0, st>>>(sa);
   SMCT_LAUNCH_CHECK("scatter_grads_kernel");
+  if (multi && io->noise_K) {   // per-dimension log-variance gradients from the forward's recorded noises
+    SMCT_CUDA(cudaMemsetAsync(colacc, 0, (size_t)4 * 256 * sizeof(double), st));
+    const long long rows = (long long)B * P * S;
+    const float* nz[4] = {io->noise_K, io->noise_q, io->noise_V, io->noise_z};
+    const float* lv[4] = {params->logvar_k, params->logvar_q, params->logvar_v, params->logvar_z};
+    float* gv[4] = {grads->logvar_k, grads->logvar_q, grads->logvar_v, grads->logvar_z};
+    const float logdet_d = (loss_variant == SMCT_LOSS_CHECKOUT) ? 0.5f * (float)((double)rows * inv_n) : 0.f;
+    for (int w = 0; w < 4; ++w) {
+      if (!gv[w]) continue;
+      const int per = std::max(1, 256 / D);
+      smct::colsumsq_kernel<<<(int)std::min<long long>((rows + per - 1) / per, 148LL * 8), 256, 0, st>>>(rows, D, nz[w], colacc + 256 * w);
+      SMCT_LAUNCH_CHECK("colsumsq_kernel");
+      smct::logvar_grad_multi_kernel<<<(D + 127) / 128, 128, 0, st>>>(D, colacc + 256 * w, lv[w], inv_n, logdet_d, gv[w]);
+      SMCT_LAUNCH_CHECK("logvar_grad_multi_kernel");
+    }
+  }
   return SMCT_OK;
 }
 

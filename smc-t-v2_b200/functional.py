@@ -381,6 +381,8 @@ def backward(shape: SmctShape, params: Dict[str, torch.Tensor], x_in: torch.Tens
     io.V = _ptr(fwd["V"], torch.float32, "V")
     io.i_out = _ptr(fwd["i_out"], torch.int32, "i_out")
     io.loss_sums = _ptr(fwd.get("loss_sums"), torch.float64, "loss_sums")
+    for n in ("noise_K", "noise_q", "noise_V", "noise_z"):   # recorded noises: per-dimension log-variance gradients
+        setattr(io, n, _ptr(fwd.get(n), torch.float32, n))
     need = lib.smct_backward_workspace_bytes(ctypes.byref(shape))
     if need == 0:
         raise _lib.SmctError(-4, lib.smct_last_error().decode())

@@ -26,7 +26,17 @@ def logvar_vector(logvar):
     -> its diagonal (D,) — what add_noise uses through tf.linalg.diag_part (:104)."""
     v = logvar.value if isinstance(logvar, Variable) else torch.as_tensor(np.asarray(logvar, np.float32), device=_device())
     if v.dim() == 2:
-        return torch.diagonal(v).contiguous()
+        if not isinstance(logvar, Variable):
+            return torch.diagonal(v).contiguous()
+        # a persistent (D,) buffer per variable (stable data pointer: the optimiser keys its moments by it), refreshed from
+        # the matrix on every call; the training step writes the updated diagonal back into the matrix
+        d = getattr(logvar, "_diag", None)
+        if d is None or d.numel() != v.shape[0]:
+            d = torch.diagonal(v).contiguous().clone()
+            logvar._diag = d
+        else:
+            d.copy_(torch.diagonal(v))
+        return d
     return v.reshape(-1).contiguous()
 
 

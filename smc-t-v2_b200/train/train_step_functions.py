@@ -68,7 +68,13 @@ def train_step_SMC_T(inputs, targets, smc_transformer, optimizer, it, attention_
         # optimizer.apply_gradients(zip(gradients, trainable_variables)): only TRAINABLE variables are updated — in EM
         # mode the log-variances are plain tensors outside trainable_variables (self_attention_SMC.py:48-52)
         trainable = {v.value.data_ptr() for v in smc_transformer.trainable_variables}
-        names = sorted(n for n in grads if params[n].data_ptr() in trainable)
+        att = smc_transformer.cell.attention_smc
+
+        def is_trainable(n):
+            if n.startswith("logvar_"):   # "multi" log-variances are (D,D) diagonal matrices: the kernels see a copy of the diagonal
+                return bool(getattr(att, n).trainable)
+            return params[n].data_ptr() in trainable
+        names = sorted(n for n in grads if is_trainable(n))
         if world > 1:
             flat = torch.cat([grads[n].reshape(-1) for n in names])
             D.allreduce_sums(flat)
@@ -78,6 +84,9 @@ def train_step_SMC_T(inputs, targets, smc_transformer, optimizer, it, attention_
                 grads[n].copy_(flat[o:o + k].reshape(grads[n].shape))
                 o += k
         optimizer.apply_gradients((grads[n], params[n]) for n in names)
+        for n in names:   # write the updated diagonal back into the (D,D) variable of noise_dim = "multi"
+            if n.startswith("logvar_") and getattr(att, n).value.dim() == 2:
+                getattr(att, n).value.diagonal().copy_(params[n])
     if smc_transformer.cell.noise:
         return loss, metric
     return loss, None

@@ -19,7 +19,7 @@ PARITY_LOG = {}
 
 
 def _log_parity(name, err, tol, scale):
-    key = name.split(":")[-1]
+    key = name.split(":")[-1].split("[")[0].strip()
     r_tol = float((err / tol).max()) if err.size else 0.0
     r_scale = float(err.max() / (scale + 1e-30)) if err.size else 0.0
     old = PARITY_LOG.get(key, (0.0, 0.0, 0))
