@@ -32,7 +32,7 @@ from oracle import tf_shim  # noqa: E402
 OUT = os.path.join(ROOT, "tests", "golden")
 
 
-def run_reference(B, P, S, D, dff, V, attn_window, sigma, seed, regression=None, len_resampling=None, em=(3, 0.6)):
+def run_reference(B, P, S, D, dff, V, attn_window, sigma, seed, regression=None, len_resampling=None, em=(3, 0.6), multi=False):
     tf_shim.TRACK_GRADIENTS = True
     try:
         inst = tf_shim.install()
@@ -42,8 +42,12 @@ def run_reference(B, P, S, D, dff, V, attn_window, sigma, seed, regression=None,
         from src.train.utils import EM
         model = SMC_Transformer(d_model=D, output_size=V, seq_len=S, full_model=True, dff=dff, num_layers=1, num_heads=1,
                                 attn_window=attn_window)
-        model.cell.add_SMC_parameters(dict_sigmas=dict(zip(["k", "q", "v", "z"], [sigma * 1.0, sigma * 1.3, sigma * 0.8, sigma * 1.1])),
-                                      num_particles=P)
+        base = [sigma * 1.0, sigma * 1.3, sigma * 0.8, sigma * 1.1]
+        if multi:   # noise_dim = "multi" (run_SMC_T.py:75-82): a list of d_model variances per noise -> (D,D) diagonal variables
+            sig = [[float(sv * (1.0 + 0.07 * i)) for i in range(D)] for sv in base]
+        else:
+            sig = base
+        model.cell.add_SMC_parameters(dict_sigmas=dict(zip(["k", "q", "v", "z"], sig)), num_particles=P)
         if len_resampling is not None:
             model.cell.add_stop_resampling(len_resampling)
         g = np.random.default_rng(seed + 1)
@@ -96,7 +100,8 @@ def run_reference(B, P, S, D, dff, V, attn_window, sigma, seed, regression=None,
             else:
                 parts = []
                 for noise, lv in zip(model.internal_noises, [att.logvar_k, att.logvar_q, att.logvar_v, att.logvar_z]):
-                    parts.append(0.5 * (noise * noise / torch.exp(lv.value)).sum(-1))
+                    var = torch.exp(lv.value) if lv.value.dim() == 0 else torch.exp(torch.diagonal(lv.value))
+                    parts.append(0.5 * (noise * noise / var).sum(-1))
                 classic = (0.5 / regression["sigma_obs"]) * ((ty - pred_r) ** 2).sum(-1).mean()
                 total = torch.stack(parts).sum(0).mean() + classic
         c = model.cell
@@ -115,11 +120,18 @@ def run_reference(B, P, S, D, dff, V, attn_window, sigma, seed, regression=None,
         for n, gr in zip(names, grads):
             if n == "logvar_z":
                 continue
-            out_g[n] = (torch.zeros_like(named[n].value) if gr is None else gr).detach().numpy().astype(np.float32)
-        params = {n: v.numpy().astype(np.float32).copy() for n, v in named.items()}
+            gr = torch.zeros_like(named[n].value) if gr is None else gr
+            if n.startswith("logvar_") and gr.dim() == 2:
+                gr = torch.diagonal(gr)          # only the diagonal of the (D,D) variable is used (tf.linalg.diag_part)
+            out_g[n] = gr.detach().numpy().astype(np.float32).copy()
+        params = {n: (np.diagonal(v.numpy()) if (n.startswith("logvar_") and v.numpy().ndim == 2) else v.numpy()).astype(np.float32).copy()
+                  for n, v in named.items()}
         if regression is None:
             params["b_in"] = np.zeros(D, np.float32)
         # ---- EM on the model after the forward (src/train/utils.py:22-51) ----
+        if multi:   # the reference's EM mode is scalar-only
+            return dict(params=params, grads=out_g, x_in=x_in, y=y, eps=eps, u=u, loss_total=float(total), loss_classic=float(classic),
+                        pred_resampl=pred_r.detach().numpy(), noise_z=model.noise_z.numpy(), em=None, lv_before=None, lv_after=None)
         it, em_param = em
         lv_before = {n: float(getattr(att, "logvar_" + n).numpy()) for n in "kqvz"}
         with torch.no_grad():
@@ -144,6 +156,10 @@ SPECS = {
     "ref_grad_regression_d64": dict(B=1, P=24, S=6, D=64, dff=256, V=1, attn_window=None, sigma=0.5, seed=23,
                                     regression=dict(F_x=1, sigma_obs=0.5)),
     "ref_grad_checkout_classification": dict(B=3, P=8, S=6, D=16, dff=16, V=20, attn_window=None, sigma=0.2, seed=24),
+    # noise_dim = "multi": per-dimension variances, the configuration of the reference's published ROC runs
+    "ref_grad_checkout_multi": dict(B=2, P=10, S=7, D=16, dff=16, V=15, attn_window=None, sigma=0.3, seed=25, multi=True),
+    "ref_grad_regression_multi": dict(B=2, P=12, S=6, D=8, dff=16, V=2, attn_window=None, sigma=0.4, seed=26, multi=True,
+                                      regression=dict(F_x=2, sigma_obs=0.5)),
 }
 
 
@@ -153,15 +169,18 @@ def main():
         r = run_reference(**kw)
         arrays = dict(name=np.array(name), meta=np.array(repr(kw)), x_in=r["x_in"], y=r["y"], eps=r["eps"], u=r["u"],
                       loss_total=np.array(r["loss_total"]), loss_classic=np.array(r["loss_classic"]),
-                      pred_resampl=r["pred_resampl"], em=r["em"],
-                      lv_before=np.array([r["lv_before"][n] for n in "kqvz"]), lv_after=np.array([r["lv_after"][n] for n in "kqvz"]))
+                      pred_resampl=r["pred_resampl"])
+        if r["em"] is not None:
+            arrays.update(em=r["em"], lv_before=np.array([r["lv_before"][n] for n in "kqvz"]),
+                          lv_after=np.array([r["lv_after"][n] for n in "kqvz"]))
         arrays.update({"p_" + k: v for k, v in r["params"].items()})
         arrays.update({"g_" + k: v for k, v in r["grads"].items()})
         path = os.path.join(OUT, name + ".npz")
         np.savez_compressed(path, **arrays)
         gn = {k: float(np.abs(v).max()) for k, v in r["grads"].items()}
         print(path, os.path.getsize(path) // 1024, "KiB loss", r["loss_total"], "max|grad|", {k: "%.2e" % v for k, v in gn.items()})
-        print("   EM", r["lv_before"], "->", r["lv_after"])
+        if r["em"] is not None:
+            print("   EM", r["lv_before"], "->", r["lv_after"])
 
 
 if __name__ == "__main__":

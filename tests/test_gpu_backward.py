@@ -24,13 +24,14 @@ BWD_CASES = {
 }
 
 
-def _run(cfg, variant, algo="staged", seed=0):
-    p, x_in, y, eps, u = util.make_case(cfg, seed=seed, sigma2=0.5, random_bias=True)
-    shape = F.shape_from_config(cfg, logvar_dim=1, algo=algo)
+def _run(cfg, variant, algo="staged", seed=0, multi=False):
+    p, x_in, y, eps, u = util.make_case(cfg, seed=seed, sigma2=0.5, random_bias=True, multi=multi)
+    shape = F.shape_from_config(cfg, logvar_dim=util.logvar_dim(p), algo=algo)
     dp = util.dev_params(p)
     tx, ty = torch.as_tensor(x_in, device="cuda"), torch.as_tensor(y, device="cuda")
     te, tu = torch.as_tensor(eps, device="cuda"), torch.as_tensor(u, device="cuda")
-    fwd = F.forward(shape, dp, tx, ty, te, tu, want=("i_out", "loss_sums"))
+    want = ("i_out", "loss_sums") + (("noise_K", "noise_q", "noise_V", "noise_z") if multi else ())
+    fwd = F.forward(shape, dp, tx, ty, te, tu, want=want)
     grads = F.backward(shape, dp, tx, ty, fwd, eps=te, loss_variant=variant)
     torch.cuda.synchronize()
     i_out = fwd["i_out"].cpu().numpy()
@@ -57,6 +58,17 @@ def test_backward_matches_autograd(name, variant):
     cfg = BWD_CASES[name]
     got, ref, p = _run(cfg, variant)
     _compare(name, got, ref)
+
+
+@pytest.mark.parametrize("variant", ["pyc", "checkout"])
+@pytest.mark.parametrize("name", ["c3", "window_stop", "classification", "d64_p70"])
+def test_backward_per_dimension_logvars(name, variant):
+    """noise_dim = "multi" (self_attention_SMC.py:57-61,98-107): per-dimension noise scales in the replayed forward, per-
+    dimension 1/sigma^2 in the K / V loss terms, and (D,) log-variance gradients from the forward's recorded noises."""
+    cfg = BWD_CASES[name]
+    got, ref, p = _run(cfg, variant, multi=True, algo="fused" if name == "d64_p70" else "staged")
+    assert got["logvar_k"].shape == (cfg.D,) and np.abs(ref["logvar_k"]).max() > 0
+    _compare(name + ":multi", got, ref)
 
 
 def test_backward_from_fused_forward_and_chunk_accumulation():

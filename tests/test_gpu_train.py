@@ -176,3 +176,28 @@ def test_forecast_multistep_matches_oracle_rollout():
     assert got.shape == ref.shape == (B, P, future_len, 1)
     util.assert_close("forecast preds_future", got, ref)
     util.assert_close("forecast mean", mean.cpu().numpy(), ref.mean(axis=1))
+
+
+def test_train_per_dimension_variances():
+    """-noise_dim multi (the reference's published ROC runs): the (D,D) diagonal log-variance variables train — Adam moves
+    their diagonals, keeps its moments between steps, and leaves the off-diagonal entries alone."""
+    from smct_b200.algos.run_SMC_T import SMCTAlgo, default_args
+    from smct_b200.train.optimizers import Adam
+    from smct_b200.train.train_step_functions import train_step_SMC_T
+    ds = TinyDataset(n_train=1, n_val=1)
+    algo = SMCTAlgo(dataset=ds, args=default_args(d_model=8, dff=8, particles=6, sigmas=0.5, noise_dim="multi", ep=1, bs=8))
+    m = algo.smc_transformer
+    att = m.cell.attention_smc
+    assert tuple(att.logvar_k.shape) == (8, 8) and att.logvar_dim() == 8
+    m.seed = 4
+    inp, tar, _ = algo.train_dataset[0]
+    opt = Adam(1e-2)
+    lv0 = att.logvar_k.numpy().copy()
+    losses = [float(train_step_SMC_T(inp, tar, m, opt, it=i + 1)[0]) for i in range(5)]
+    n_slots = len(opt._slots)
+    losses.append(float(train_step_SMC_T(inp, tar, m, opt, it=6)[0]))
+    assert len(opt._slots) == n_slots == len(m.trainable_variables)          # moments are kept, not re-created
+    lv1 = att.logvar_k.numpy()
+    off = ~np.eye(8, dtype=bool)
+    assert np.array_equal(lv1[off], lv0[off]) and np.all(np.diagonal(lv1) != np.diagonal(lv0))
+    assert np.all(np.isfinite(losses)) and losses[-1] < losses[0], losses
