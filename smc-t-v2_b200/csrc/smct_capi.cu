@@ -188,7 +188,23 @@ int launch_seq_t(const smct::SeqArgs& g, cudaStream_t st) {
   if (attr_once.need()) {
     SMCT_CUDA(cudaFuncSetAttribute(smct::seq_forward_kernel<KD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   }
-  smct::seq_forward_kernel<KD><<<g.step.B, KD <= 2 ? smct::NT_WIDE : smct::NT, smem, st>>>(g);
+  const int nthreads = KD <= 2 ? smct::NT_WIDE : smct::NT;
+  if (g.cl <= 1) {
+    smct::seq_forward_kernel<KD><<<g.step.B, nthreads, smem, st>>>(g);
+  } else {   // one thread-block cluster per sequence
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)(g.step.B * g.cl), 1, 1);
+    cfg.blockDim = dim3((unsigned)nthreads, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)g.cl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    SMCT_CUDA(cudaLaunchKernelEx(&cfg, smct::seq_forward_kernel<KD>, g));
+  }
   SMCT_LAUNCH_CHECK("seq_forward_kernel");
   return SMCT_OK;
 }
@@ -253,6 +269,11 @@ int forward_staged(const smct_shape& s, const smct_params& pr, const smct_io& io
     g.seed = io.seed;
     g.K0 = io.K; g.V0 = io.V; g.R0 = io.R; g.K2 = K2; g.V2 = V2; g.R2 = R2;
     g.logw_ws = logw; g.idx_ws = idx;
+    {   // CTAs per sequence: one per particle tile, rounded up to a power of two, at most a portable cluster (8)
+      const int tiles = (P + smct::PT - 1) / smct::PT;
+      g.cl = 1;
+      while (g.cl < tiles && g.cl < 8) g.cl *= 2;
+    }
     g.pred = io.pred; g.noise_q = io.noise_q; g.noise_z = io.noise_z; g.attn = io.attn; g.w = io.w; g.logw_out = io.logw;
     g.i_out = io.i_out;
     int rc;
@@ -550,9 +571,13 @@ int smct_forward(const smct_shape* shape, const smct_params* params, const smct_
     if (!io->y) return fail(SMCT_ERR_INVALID, "y (targets) required");
     return forward_fused(*shape, *params, *io, workspace, workspace_bytes, st, algo);
   }
-  // the per-sequence single-launch variant serves shapes with one particle tile per sequence (P <= 32), where the staged
-  // loop is launch-bound (measured on B200: C1 0.69 -> 0.45 ms; with several tiles per sequence it serialises them: slower)
-  const bool seq = (algo == SMCT_ALGO_STAGED_SEQ) || (shape->algo == SMCT_ALGO_AUTO && shape->P <= smct::PT);
+  // the per-sequence single-launch variant (a thread-block cluster per sequence, one CTA per particle tile) serves the
+  // reference's own small shapes; with more than 8 tiles per sequence (P > 256) a CTA would serialise several tiles
+  // (measured on B200: C1 0.69 -> 0.44 ms, C2 0.91 -> 0.86 ms; C3 — 256 sequences x 2 tiles, more CTAs than SMs — is
+  // faster on the per-stage kernels: 2.75 vs 3.75 ms, so AUTO takes the cluster form only while every CTA gets its own SM)
+  const int seq_tiles = (shape->P + smct::PT - 1) / smct::PT;
+  const bool seq = (algo == SMCT_ALGO_STAGED_SEQ) ||
+                   (shape->algo == SMCT_ALGO_AUTO && (seq_tiles == 1 || (seq_tiles <= 8 && (long long)shape->B * seq_tiles <= 148)));
   return forward_staged(*shape, *params, *io, workspace, workspace_bytes, st, seq);
 }
 

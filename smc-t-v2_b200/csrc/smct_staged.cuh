@@ -610,6 +610,7 @@ __global__ void __launch_bounds__(256) gather_kernel(const GatherArgs a) {
 struct SeqArgs {
   StepArgs step;                 // step-independent fields (fill_step_common) + loss_sums
   int attn_window, len_resampling, normalise, n_gather;
+  int cl;                        // CTAs per sequence (thread-block cluster size; 1 = no cluster)
   const float *xln, *q_, *k_, *v_;   // (B,S,D)
   const void* y;                 // (B,S,Fy) f32 | (B,S) i32
   const float* eps;              // optional (4,S,B,P,D)
@@ -622,12 +623,27 @@ struct SeqArgs {
   int* i_out;
 };
 
+// A sequence is served by a thread-block CLUSTER of CL CTAs (CL = 1: the plain one-CTA-per-sequence form): CTA `rank`
+// owns the particle tiles rank, rank + CL, ... of every timestep and the matching share of the ancestor gather; the draw
+// (which needs all P log-weights) runs on rank 0.  The cluster barrier (release / acquire at cluster scope) orders the
+// global-memory traffic between the phases, so the S x (step, draw, gather) loop of C2 / C3 (P = 100 / 60: 4 / 2 tiles)
+// is ONE launch instead of 74 without serialising the tiles of a sequence on one SM.
+__device__ __forceinline__ void seq_cluster_sync(int cl) {
+  if (cl > 1) {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  } else {
+    __syncthreads();
+  }
+}
+
 template <int KD>
 __global__ void __launch_bounds__(KD <= 2 ? NT_WIDE : NT) seq_forward_kernel(const SeqArgs g) {
   extern __shared__ float sm[];
   __shared__ float scratch[32];
   __shared__ double total_s;
-  const int b = blockIdx.x, tid = threadIdx.x;
+  const int CL = g.cl;
+  const int b = blockIdx.x / CL, rank = blockIdx.x % CL, tid = threadIdx.x;
   const int B = g.step.B, P = g.step.P, S = g.step.S, D = g.step.D, H = g.step.H, Fy = g.step.Fy;
   const size_t BPD = (size_t)B * P * D, BP = (size_t)B * P;
   float *Kc, *Vc, *Rc, *Ka, *Va, *Ra;
@@ -654,11 +670,12 @@ __global__ void __launch_bounds__(KD <= 2 ? NT_WIDE : NT) seq_forward_kernel(con
     a.attn = g.attn ? g.attn + (size_t)t * S : nullptr;
     a.attn_st_bp = (long long)H * S * S; a.attn_st_h = (long long)S * S;
     a.logw = g.logw_ws;
-    for (int p0 = 0; p0 < P; p0 += PT) {
+    for (int p0 = rank * PT; p0 < P; p0 += CL * PT) {
       step_tile<KD>(a, b, p0, sm);
       __syncthreads();
     }
     if (a.noise_on) {
+      seq_cluster_sync(CL);   // the log-weights of all tiles are in global memory
       ResampleArgs r;
       r.B = B; r.P = P; r.normalise = g.normalise;
       r.logw = g.logw_ws;
@@ -670,25 +687,26 @@ __global__ void __launch_bounds__(KD <= 2 ? NT_WIDE : NT) seq_forward_kernel(con
       r.logits_out = nullptr;
       r.i_out = g.idx_ws;
       r.i_out2 = g.i_out ? g.i_out + (size_t)t * BP : nullptr;
-      resample_seq(r, b, reinterpret_cast<double*>(sm), scratch, &total_s);
-      __syncthreads();
+      if (rank == 0) resample_seq(r, b, reinterpret_cast<double*>(sm), scratch, &total_s);
+      seq_cluster_sync(CL);   // the ancestor indices are in global memory
       if (g.len_resampling < 0 || t < g.len_resampling) {
         // ancestor gather of this sequence: rows 0..t of K, V, R (transformer_utils.py:39-47)
         const long long rowlen = (long long)(t + 1) * D, stride = (long long)S * D;
-        const long long n = (long long)P * rowlen;
+        const int m_per = (P + CL - 1) / CL, m_lo = rank * m_per, m_hi = min(P, m_lo + m_per);   // this CTA's destination particles
+        const long long n = (long long)max(0, m_hi - m_lo) * rowlen;
         const int* idx = g.idx_ws + (size_t)b * P;
         for (int z = 0; z < 3; ++z) {
           const float* src = (z == 0 ? Kc : (z == 1 ? Vc : Rc)) + (size_t)b * P * stride;
           float* dst = (z == 0 ? Ka : (z == 1 ? Va : Ra)) + (size_t)b * P * stride;
           for (long long i = tid; i < n; i += (long long)blockDim.x) {
-            const int m = (int)(i / rowlen);
-            const long long off = i - (long long)m * rowlen;
+            const int m = m_lo + (int)(i / rowlen);
+            const long long off = i - (long long)(m - m_lo) * rowlen;
             dst[(long long)m * stride + off] = src[(long long)idx[m] * stride + off];
           }
         }
         float* tp;
         tp = Kc; Kc = Ka; Ka = tp; tp = Vc; Vc = Va; Va = tp; tp = Rc; Rc = Ra; Ra = tp;
-        __syncthreads();
+        seq_cluster_sync(CL);   // the gathered rows are visible to the CTAs that own them in the next step
       }
     }
   }
