@@ -114,6 +114,9 @@ typedef struct smct_io {
   float *noise_K, *noise_V;/* optional (B,P,S,D) K - wk(X), V - wv(X) (SMC_Transformer.py:235-236) */
   float *attn;             /* optional (B,P,H,S,S) */
   double *loss_sums;       /* optional (8): sum n^2/sigma^2 for K,q,V,z; sum (y-pred_resampl)^2; 3 spare */
+  const float *classic_w;  /* optional (B,S), smct_backward only: weight of the classic-loss term of row (b,s) relative to the
+                            * uniform 1/(B*P*S) mean — the attention_mask weighting of compute_classic_loss
+                            * (SMC_Transformer.py:158-163): mask[b,s] * (global B*S) / (global sum of the mask) */
 } smct_io;
 
 int smct_abi_version(void);
@@ -220,10 +223,11 @@ int smct_encode(const smct_shape *shape, const smct_params *params, const void *
 int smct_tc_selftest(const float *A, const float *W, float *D, void *scratch, void *stream);
 
 /* compute_classic_loss — SMC_Transformer.py:148-164 (sparse CE, checkout) / regression-era MSE form (pyc).
- * out[0] += sum_{b,p,s} ||y[b,s]-pred[b,p,s]||^2 (gaussian; y (B,S,F_y) f32)
- *        or sum_{b,p,s} CE(pred[b,p,s,:], y[b,s]) (classification; y (B,S) i32).  pred (B,P,S,F_y). */
+ * out[0] += sum_{b,p,s} m[b,s] * ||y[b,s]-pred[b,p,s]||^2 (gaussian; y (B,S,F_y) f32)
+ *        or sum_{b,p,s} m[b,s] * CE(pred[b,p,s,:], y[b,s]) (classification; y (B,S) i32).  pred (B,P,S,F_y).
+ * mask (B,S) f32 is the attention_mask of the reference's masked mean (:158-163); NULL = all ones. */
 int smct_classic_loss(int32_t B, int32_t P, int32_t S, int32_t F_y, int32_t weights_mode, const float *pred,
-                      const void *y, double *out, void *stream);
+                      const void *y, const float *mask, double *out, void *stream);
 
 #ifdef __cplusplus
 }

@@ -32,7 +32,8 @@ from oracle import tf_shim  # noqa: E402
 OUT = os.path.join(ROOT, "tests", "golden")
 
 
-def run_reference(B, P, S, D, dff, V, attn_window, sigma, seed, regression=None, len_resampling=None, em=(3, 0.6), multi=False):
+def run_reference(B, P, S, D, dff, V, attn_window, sigma, seed, regression=None, len_resampling=None, em=(3, 0.6), multi=False,
+                  masked=False):
     tf_shim.TRACK_GRADIENTS = True
     try:
         inst = tf_shim.install()
@@ -88,15 +89,20 @@ def run_reference(B, P, S, D, dff, V, attn_window, sigma, seed, regression=None,
             return torch.from_numpy(u[t])
         rng.normal_fn, rng.uniform_fn = normal_fn, uniform_fn
         tx, ty = torch.from_numpy(x_in), torch.from_numpy(y)
+        mask = None
+        if masked:   # NLP padding mask (B,1,S,1): ones up to a per-sequence length, zeros behind it
+            lens = g.integers(max(1, S // 2), S + 1, size=B)
+            mask = (np.arange(S)[None, :] < lens[:, None]).astype(np.int32).reshape(B, 1, S, 1)
+        tmask = None if mask is None else torch.from_numpy(mask)
         with tf.GradientTape() as tape:
-            (pred, pred_r), (K, Vv, R), w = model(inputs=tx, targets=ty, attention_mask=None)
+            (pred, pred_r), (K, Vv, R), w = model(inputs=tx, targets=ty, attention_mask=tmask)
             assert cnt["n"] == 4 * (S + 1) and cnt["c"] == S + 1
             # the recorded noise_z enters the loss detached (module docstring)
             model.noise_z = model.noise_z.detach()
             model.internal_noises = [model.noise_K_resampled, model.noise_q, model.noise_V_resampled, model.noise_z]
             att = model.cell.attention_smc
             if regression is None:
-                total, classic = model.compute_SMC_loss(inputs=None, targets=ty, predictions=pred_r)
+                total, classic = model.compute_SMC_loss(inputs=None, targets=ty, predictions=pred_r, attention_mask=tmask)
             else:
                 parts = []
                 for noise, lv in zip(model.internal_noises, [att.logvar_k, att.logvar_q, att.logvar_v, att.logvar_z]):
@@ -131,7 +137,8 @@ def run_reference(B, P, S, D, dff, V, attn_window, sigma, seed, regression=None,
         # ---- EM on the model after the forward (src/train/utils.py:22-51) ----
         if multi:   # the reference's EM mode is scalar-only
             return dict(params=params, grads=out_g, x_in=x_in, y=y, eps=eps, u=u, loss_total=float(total), loss_classic=float(classic),
-                        pred_resampl=pred_r.detach().numpy(), noise_z=model.noise_z.numpy(), em=None, lv_before=None, lv_after=None)
+                        pred_resampl=pred_r.detach().numpy(), noise_z=model.noise_z.numpy(), em=None, lv_before=None, lv_after=None,
+                        mask=mask)
         it, em_param = em
         lv_before = {n: float(getattr(att, "logvar_" + n).numpy()) for n in "kqvz"}
         with torch.no_grad():
@@ -143,7 +150,7 @@ def run_reference(B, P, S, D, dff, V, attn_window, sigma, seed, regression=None,
         lv_after = {n: float(getattr(att, "logvar_" + n)) for n in "kqvz"}
         return dict(params=params, grads=out_g, x_in=x_in, y=y, eps=eps, u=u, loss_total=float(total), loss_classic=float(classic),
                     pred_resampl=pred_r.detach().numpy(), noise_z=model.noise_z.numpy(),
-                    em=np.array([it, em_param], np.float64), lv_before=lv_before, lv_after=lv_after)
+                    em=np.array([it, em_param], np.float64), lv_before=lv_before, lv_after=lv_after, mask=mask)
     finally:
         tf_shim.TRACK_GRADIENTS = False
 
@@ -158,6 +165,8 @@ SPECS = {
     "ref_grad_checkout_classification": dict(B=3, P=8, S=6, D=16, dff=16, V=20, attn_window=None, sigma=0.2, seed=24),
     # noise_dim = "multi": per-dimension variances, the configuration of the reference's published ROC runs
     "ref_grad_checkout_multi": dict(B=2, P=10, S=7, D=16, dff=16, V=15, attn_window=None, sigma=0.3, seed=25, multi=True),
+    # attention_mask: the masked mean of compute_classic_loss (SMC_Transformer.py:158-163)
+    "ref_grad_checkout_masked": dict(B=4, P=6, S=8, D=16, dff=16, V=12, attn_window=None, sigma=0.2, seed=27, masked=True),
     "ref_grad_regression_multi": dict(B=2, P=12, S=6, D=8, dff=16, V=2, attn_window=None, sigma=0.4, seed=26, multi=True,
                                       regression=dict(F_x=2, sigma_obs=0.5)),
 }
@@ -170,6 +179,8 @@ def main():
         arrays = dict(name=np.array(name), meta=np.array(repr(kw)), x_in=r["x_in"], y=r["y"], eps=r["eps"], u=r["u"],
                       loss_total=np.array(r["loss_total"]), loss_classic=np.array(r["loss_classic"]),
                       pred_resampl=r["pred_resampl"])
+        if r.get("mask") is not None:
+            arrays["mask"] = r["mask"]
         if r["em"] is not None:
             arrays.update(em=r["em"], lv_before=np.array([r["lv_before"][n] for n in "kqvz"]),
                           lv_after=np.array([r["lv_after"][n] for n in "kqvz"]))

@@ -135,7 +135,7 @@ def forward(cfg, p, x_in, y, eps=None, u=None, generator=None, i_forced=None):
                 noise_K_resampled=noise_K, noise_V_resampled=noise_V)
 
 
-def loss_and_grads(cfg, p_np, x_in, y, eps, i_forced, variant="pyc"):
+def loss_and_grads(cfg, p_np, x_in, y, eps, i_forced, variant="pyc", mask=None):
     """Gradient oracle: torch autograd through this restatement (fp64), with injected draws and
     teacher-forced ancestor indices.  Returns (loss, {name: grad ndarray}).  The reference takes
     tape.gradient(loss, trainable_variables) of exactly this graph (train_step_functions.py:43-63)."""
@@ -162,10 +162,20 @@ def loss_and_grads(cfg, p_np, x_in, y, eps, i_forced, variant="pyc"):
         if classification:   # compute_classic_loss (SMC_Transformer.py:148-164): sparse CE of the resampled logits
             pr = out["pred_resampl"]
             tgt = ty.reshape(B, 1, S).repeat(1, cfg.P, 1).long()
-            loss = tot + torch.nn.functional.cross_entropy(pr.reshape(-1, pr.shape[-1]), tgt.reshape(-1))
+            ce = torch.nn.functional.cross_entropy(pr.reshape(-1, pr.shape[-1]), tgt.reshape(-1), reduction="none").reshape(B, cfg.P, S)
+            if mask is None:
+                loss = tot + ce.mean()
+            else:   # masked mean of compute_classic_loss (SMC_Transformer.py:158-163): the mask is tiled over the particles
+                m = torch.as_tensor(np.asarray(mask, np.float64)).reshape(B, 1, S).expand(B, cfg.P, S)
+                loss = tot + (ce * m).sum() / m.sum()
         else:
             diff = ty.reshape(B, 1, S, cfg.F_y) - out["pred_resampl"]
-            loss = tot + (0.5 / cfg.sigma_obs) * diff.square().sum(-1).mean()
+            se = (0.5 / cfg.sigma_obs) * diff.square().sum(-1)
+            if mask is None:
+                loss = tot + se.mean()
+            else:
+                m = torch.as_tensor(np.asarray(mask, np.float64)).reshape(B, 1, S).expand(B, cfg.P, S)
+                loss = tot + (se * m).sum() / m.sum()
         names = list(tp)
         grads = torch.autograd.grad(loss, [tp[n] for n in names], allow_unused=True)
     finally:

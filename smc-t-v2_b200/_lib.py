@@ -46,7 +46,7 @@ class SmctIO(ctypes.Structure):
     _fields_ = [("x_in", VP), ("y", VP), ("eps", VP), ("u", VP), ("i_forced", VP), ("seed", ctypes.c_uint64),
                 ("pred", VP), ("pred_resampl", VP), ("K", VP), ("V", VP), ("R", VP), ("w", VP), ("i_out", VP),
                 ("logw", VP), ("noise_q", VP), ("noise_z", VP), ("noise_K", VP), ("noise_V", VP), ("attn", VP),
-                ("loss_sums", VP)]
+                ("loss_sums", VP), ("classic_w", VP)]
 
 
 class SmctError(RuntimeError):
@@ -85,7 +85,7 @@ def _declare(lib):
         "smct_sumsq_scaled": (ctypes.c_int, [i64, i32, VP, VP, i32, VP, VP]),
         "smct_tc_selftest": (ctypes.c_int, [VP, VP, VP, VP, VP]),
         "smct_encode": (ctypes.c_int, [SP, PP, VP, VP, VP, VP]),
-        "smct_classic_loss": (ctypes.c_int, [i32, i32, i32, i32, i32, VP, VP, VP, VP]),
+        "smct_classic_loss": (ctypes.c_int, [i32, i32, i32, i32, i32, VP, VP, VP, VP, VP]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)  # AttributeError if the symbol is missing: loud by design

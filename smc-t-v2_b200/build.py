@@ -57,15 +57,34 @@ def needs_build():
 
 
 def build(force=False, verbose=False):
-    """Compile the library for sm_100a.  Returns the path of the .so."""
+    """Compile the library for sm_100a.  Returns the path of the .so.  Several processes of one job (torchrun ranks) may
+    call this at once: the compile runs under an exclusive file lock and the others re-check the hash afterwards."""
     if not force and not needs_build():
         return LIB
+    import fcntl
+    with open(os.path.join(HERE, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not needs_build():   # another process built it while this one waited
+                return LIB
+            return _build_locked(verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(verbose):
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise RuntimeError("libsmct_b200.so is missing or was built from other sources (embedded hash %s, tree %s) and nvcc "
                            "is not available to rebuild it" % (built_hash(), source_hash()))
-    cmd = [nvcc] + NVCC_FLAGS + ['-DSMCT_SOURCE_HASH="%s"' % source_hash(), "-o", LIB] + SOURCES
+    tmp = LIB + ".tmp.%d" % os.getpid()
+    cmd = [nvcc] + NVCC_FLAGS + ['-DSMCT_SOURCE_HASH="%s"' % source_hash(), "-o", tmp] + SOURCES
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode == 0:
+        os.replace(tmp, LIB)       # atomic: a concurrently loading process never sees a half-written library
+    elif os.path.exists(tmp):
+        os.remove(tmp)
+    cmd[-len(SOURCES) - 1] = LIB
     log = os.path.join(HERE, "build.log")
     with open(log, "w") as f:
         f.write(" ".join(cmd) + "\n" + r.stdout)

@@ -50,6 +50,7 @@ struct BwdArgs {
   const float *X, *xln, *q_, *kx, *vx;   // (B,S,D) rows (rows_kernel)
   const void* y;                          // (B,S,Fy) f32 (gaussian) | (B,S) i32 class ids (classification)
   const float* eps;                       // optional (4,S,B,P,D)
+  const float* classic_w;                 // optional (B,S): weight of the classic-loss term of row (b,s) (masked losses)
   smct_params p;
   const float *WzT, *W1T, *W2T;           // transposed weights
   const float *K, *V;                     // (B,P,S,D) final states
@@ -393,8 +394,9 @@ __global__ void __launch_bounds__(NT) bwd_dense_kernel(const BwdArgs a) {
 #pragma unroll
           for (int k = 0; k < KD; ++k) { const int d = lane + 32 * k; if (d < D) part = fmaf(r[k], __ldg(a.p.Wo + (long long)d * Fy + f), part); }
           const float pr = warp_sum(part);
-          const float dpred = ce ? (expf(pr - mx) / se - (f == ytok ? 1.f : 0.f)) * (a.inv_n * rm[pl])
-                                 : (pr - ((const float*)a.y)[(long long)rbs[pl] * Fy + f]) * (c_obs * rm[pl]);   // m final particles share this node
+          const float cw = a.classic_w ? a.classic_w[rbs[pl]] : 1.f;   // attention_mask weighting of compute_classic_loss
+          const float dpred = ce ? (expf(pr - mx) / se - (f == ytok ? 1.f : 0.f)) * (a.inv_n * rm[pl] * cw)
+                                 : (pr - ((const float*)a.y)[(long long)rbs[pl] * Fy + f]) * (c_obs * rm[pl] * cw);   // m final particles share this node
 #pragma unroll
           for (int k = 0; k < KD; ++k) {
             const int d = lane + 32 * k;

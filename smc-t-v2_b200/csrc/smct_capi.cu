@@ -866,7 +866,7 @@ int smct_backward(const smct_shape* shape, const smct_params* params, const smct
   a.ln_eps = s.ln_eps; a.sigma_obs = s.sigma_obs; a.inv_n = inv_n; a.sqrtD = sqrtf((float)D);
   a.b_global0 = s.b_global0; a.seed = io->seed;
   a.x_in = io->x_in; a.X = X; a.xln = xln; a.q_ = q_; a.kx = kx; a.vx = vx;
-  a.y = io->y; a.eps = io->eps; a.p = *params; a.WzT = WzT; a.W1T = W1T; a.W2T = W2T;
+  a.y = io->y; a.eps = io->eps; a.classic_w = io->classic_w; a.p = *params; a.WzT = WzT; a.W1T = W1T; a.W2T = W2T;
   a.K = io->K; a.V = io->V; a.i_out = io->i_out; a.anc = anc; a.node_off = node_off; a.node_bs = node_bs; a.node_p = node_p; a.node_L = node_L; a.node_m = node_m; a.Zm = Zm; a.dZm = dZm; a.Qm = Qm; a.stat = stat;
   a.dq_sum = dq_sum; a.dk_sum = dk_sum; a.dv_sum = dv_sum; a.dxln_sum = dxln_sum; a.dkx_sum = dkx_sum; a.dvx_sum = dvx_sum;
   a.rep = rep; a.nrep = BWD_NREP; a.lay = lay;
@@ -933,11 +933,11 @@ int smct_tc_selftest(const float* A, const float* W, float* D, void* scratch, vo
 }
 
 int smct_classic_loss(int32_t B, int32_t P, int32_t S, int32_t F_y, int32_t weights_mode, const float* pred,
-                      const void* y, double* out, void* stream) {
+                      const void* y, const float* mask, double* out, void* stream) {
   if (B < 1 || P < 1 || S < 1 || F_y < 1 || !pred || !y || !out) return fail(SMCT_ERR_INVALID, "smct_classic_loss: bad arguments");
   const long long rows = (long long)B * P * S;
   smct::classic_loss_kernel<<<(int)std::min<long long>((rows + 255) / 256, 148 * 8), 256, 0, (cudaStream_t)stream>>>(
-      B, P, S, F_y, weights_mode, pred, y, out);
+      B, P, S, F_y, weights_mode, pred, y, mask, out);
   SMCT_LAUNCH_CHECK("classic_loss_kernel");
   return SMCT_OK;
 }

@@ -820,7 +820,7 @@ __global__ void logweights_kernel(int B, int P, int Fy, int mode, float sigma_ob
 
 // sum over (b,p,s) rows of ||y[b,s]-pred[b,p,s]||^2 (gaussian) or of the sparse cross-entropy (classification)
 __global__ void __launch_bounds__(256) classic_loss_kernel(int B, int P, int S, int Fy, int mode, const float* pred,
-                                                           const void* y, double* out) {
+                                                           const void* y, const float* mask, double* out) {
   __shared__ double red[8];
   const long long rows = (long long)B * P * S;
   double acc = 0.0;
@@ -832,13 +832,14 @@ __global__ void __launch_bounds__(256) classic_loss_kernel(int B, int P, int S, 
       const float* yr = (const float*)y + ((long long)b * S + s) * Fy;
       float sq = 0.f;
       for (int f = 0; f < Fy; ++f) { const float d = yr[f] - pr[f]; sq = fmaf(d, d, sq); }
-      acc += (double)sq;
+      acc += (double)sq * (mask ? (double)mask[(long long)b * S + s] : 1.0);
     } else {
       float mx = -INFINITY;
       for (int f = 0; f < Fy; ++f) mx = fmaxf(mx, pr[f]);
       float se = 0.f;
       for (int f = 0; f < Fy; ++f) se += expf(pr[f] - mx);
-      acc += (double)(mx + logf(se) - pr[clamp_index(((const int*)y)[(long long)b * S + s], Fy)]);
+      acc += (double)(mx + logf(se) - pr[clamp_index(((const int*)y)[(long long)b * S + s], Fy)]) *
+             (mask ? (double)mask[(long long)b * S + s] : 1.0);
     }
   }
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(SMCT_FULL_MASK, acc, o);

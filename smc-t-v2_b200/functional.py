@@ -317,15 +317,18 @@ def sumsq_scaled(noise: torch.Tensor, logvar: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def classic_loss_sum(pred: torch.Tensor, y: torch.Tensor, weights="gaussian") -> torch.Tensor:
-    """sum over (b,p,s) of ||y-pred||^2 (gaussian) or of the sparse cross-entropy (classification), fp64."""
+def classic_loss_sum(pred: torch.Tensor, y: torch.Tensor, weights="gaussian", mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """sum over (b,p,s) of mask[b,s] * ||y-pred||^2 (gaussian) or of mask[b,s] * sparse cross-entropy (classification),
+    fp64.  mask (B,S) f32 (the reference's attention_mask, SMC_Transformer.py:158-163) or None."""
     require_cuda()
     lib = _lib.load()
     B, P, S, Fy = pred.shape
     out = torch.zeros((1,), dtype=torch.float64, device=pred.device)
     y_dtype = torch.int32 if weights == "classification" else torch.float32
+    if mask is not None and tuple(mask.shape) != (B, S):
+        raise ValueError("mask must have shape (B,S)")
     check(lib.smct_classic_loss(B, P, S, Fy, WEIGHTS[weights], _ptr(pred, torch.float32, "pred"), _ptr(y, y_dtype, "y"),
-                                _ptr(out), _stream()))
+                                _ptr(mask, torch.float32, "mask"), _ptr(out), _stream()))
     return out
 
 
@@ -356,7 +359,7 @@ _bws_cache: Dict[int, torch.Tensor] = {}
 
 def backward(shape: SmctShape, params: Dict[str, torch.Tensor], x_in: torch.Tensor, y: torch.Tensor, fwd: dict,
              eps: Optional[torch.Tensor] = None, seed: int = 0, inv_n: Optional[float] = None, loss_variant="pyc",
-             grads: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
+             grads: Optional[Dict[str, torch.Tensor]] = None, classic_w: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
     """tape.gradient(loss, trainable_variables) through smct_backward.  `fwd` is the dict returned by forward()
     on the same shape/params/inputs/randomness with want=("i_out","loss_sums").  Gradients are accumulated into
     `grads` (created zero-filled when None).  inv_n defaults to 1/(B*P*S) of this call."""
@@ -381,6 +384,9 @@ def backward(shape: SmctShape, params: Dict[str, torch.Tensor], x_in: torch.Tens
     io.V = _ptr(fwd["V"], torch.float32, "V")
     io.i_out = _ptr(fwd["i_out"], torch.int32, "i_out")
     io.loss_sums = _ptr(fwd.get("loss_sums"), torch.float64, "loss_sums")
+    if classic_w is not None and tuple(classic_w.shape) != (shape.B, shape.S):
+        raise ValueError("classic_w must have shape (B,S)")
+    io.classic_w = _ptr(classic_w, torch.float32, "classic_w")
     for n in ("noise_K", "noise_q", "noise_V", "noise_z"):   # recorded noises: per-dimension log-variance gradients
         setattr(io, n, _ptr(fwd.get(n), torch.float32, n))
     need = lib.smct_backward_workspace_bytes(ctypes.byref(shape))

@@ -57,6 +57,7 @@ class SMC_Transformer:
         # "checkout" (z - z_, self_attention_SMC.py:190) for integer tokens.  Gradients need "pyc".
         self.noise_z_mode = None
         self._last_forward = None
+        self._last_mask = None           # (B,S) attention mask of the last call (weights the classic loss / its gradient)
         self.algo = "auto"
         self.seed = None                 # int -> reproducible draws; None -> fresh Philox seed per call
         self._rng = np.random.default_rng(seed)
@@ -167,10 +168,10 @@ class SMC_Transformer:
         inputs (B,1,S,F_x) float | (B,1,S,1) int ; targets (B,1,S,F_y) | (B,1,S,1) int.
         Returns ((pred, pred_resampl), (K, V, R_resampl), last_filtering_weights) with the reference's shapes
         (B,P,S,F_y) / (B,P,S,D) / (B,P,S).  Keyword-only extras inject the random draws (tests)."""
-        if attention_mask is not None:
-            raise NotImplementedError("attention_mask (NLP padding, only used by the multi-layer decoder and the masked "
-                                      "losses) is out of scope")
+        # attention_mask (B,1,S,1): with num_layers == 1 the reference's forward does not look at it (only the multi-layer
+        # decoder does, SMC_Transformer.py:172-181); it weights the classic loss and the metric (compute_classic_loss)
         task, x, y, B, S, F_x, F_y = self._prep(inputs, targets)
+        self._last_mask = self._mask_bs(attention_mask, B, S)
         if S != self.seq_len:
             # the reference sizes its state with self.seq_len (SMC_Transformer.py:197); inference mutates it (run_SMC_T.py:191)
             raise ValueError("sequence length %d != model.seq_len %d" % (S, self.seq_len))
@@ -211,20 +212,29 @@ class SMC_Transformer:
         logdet = float(lv.sum().item()) * (1.0 if lv.numel() == D else D)
         return 0.5 * quad + rows * (0.5 * D * math.log(2 * math.pi) + 0.5 * logdet), rows
 
+    @staticmethod
+    def _mask_bs(attention_mask, B, S):
+        """(B,1,S,1) attention mask -> (B,S) fp32 device tensor (None stays None)."""
+        if attention_mask is None:
+            return None
+        m = _as_tensor(attention_mask).to(_device(), torch.float32).reshape(B, S).contiguous()
+        return m
+
     def compute_classic_loss(self, targets, predictions, attention_mask=None):
         """SMC_Transformer.py:148-164 (sparse CE, classification) or the regression-era
-        mean(0.5*||y-pred||^2/Sigma_obs) (pyc)."""
-        if attention_mask is not None:
-            raise NotImplementedError("masked loss is out of scope")
+        mean(0.5*||y-pred||^2/Sigma_obs) (pyc).  With an attention_mask the mean is the masked mean of :158-163:
+        sum(loss * mask) / sum(mask), the mask tiled over the particles."""
         task = "regression" if torch.is_floating_point(_as_tensor(targets)) else "classification"
         pred = predictions.to(_device(), torch.float32).contiguous()
         B, P, S, Fy = pred.shape
         t = _as_tensor(targets)
+        mask = self._mask_bs(attention_mask, B, S)
+        denom = float(B * P * S) if mask is None else float(P) * mask.sum(dtype=torch.float64)
         if task == "classification":
             y = t.reshape(B, S).to(_device(), torch.int32).contiguous()
-            return F.classic_loss_sum(pred, y, "classification") / float(B * P * S)
+            return F.classic_loss_sum(pred, y, "classification", mask=mask) / denom
         y = t.reshape(B, S, Fy).to(_device(), torch.float32).contiguous()
-        return F.classic_loss_sum(pred, y, "gaussian") * (0.5 / self.cell.Sigma_obs) / float(B * P * S)
+        return F.classic_loss_sum(pred, y, "gaussian", mask=mask) * (0.5 / self.cell.Sigma_obs) / denom
 
     def compute_SMC_loss(self, inputs, targets, predictions, attention_mask=None, variant=None):
         """compute_SMC_loss — SMC_Transformer.py:123-146.  Returns (total_loss, classic_loss) as fp64 scalar tensors.

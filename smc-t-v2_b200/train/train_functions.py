@@ -89,11 +89,11 @@ def train_SMC_transformer(smc_transformer, optimizer, EPOCHS, train_dataset, val
         for batch_val, item in enumerate(val_dataset):
             inp, tar, attn_mask = _unpack(item)
             (preds_val, preds_val_resampl), _, _ = smc_transformer(inputs=inp, targets=tar, attention_mask=attn_mask)
-            val_loss_batch, _ = smc_transformer.compute_SMC_loss(inputs=inp, targets=tar, predictions=preds_val_resampl)
+            val_loss_batch, _ = smc_transformer.compute_SMC_loss(inputs=inp, targets=tar, predictions=preds_val_resampl)   # (the reference passes no mask here, train_functions.py:207)
             val_loss[0] += _f(val_loss_batch)
             if noise:
                 if torch.is_floating_point(torch.as_tensor(np.asarray(tar)) if not isinstance(tar, torch.Tensor) else tar):
-                    val_metric = compute_mse_metric(tar, preds_val)          # regression era (pyc): MSE of the particle mean
+                    val_metric = compute_mse_metric(tar, preds_val, attention_mask=attn_mask)   # regression era (pyc): MSE of the particle mean
                 else:
                     val_metric = compute_categorical_cross_entropy(targets=tar, preds=preds_val,
                                                                    num_particles=smc_transformer.cell.num_particles,

@@ -11,14 +11,15 @@ from .. import functional as F
 from .utils import EM, compute_categorical_cross_entropy, compute_mse_metric
 
 
-def compute_gradients(smc_transformer, inputs, targets, inv_n=None, loss_variant="pyc"):
+def compute_gradients(smc_transformer, inputs, targets, inv_n=None, loss_variant="pyc", classic_w=None):
     """tape.gradient(loss, trainable_variables) for the forward pass that was just run on (inputs, targets).
     Returns {parameter name: gradient tensor} keyed like smct_params.
 
     The forward is replayed with the noise scales it actually used: `_last_forward["logvar_fwd"]` holds clones of the
     four log-variances taken at forward time.  smct_backward regenerates the q and z noises from logvar_q / logvar_z
     (-> the forward's values) and weights the K / V noise terms of the loss with exp(-logvar_k), exp(-logvar_v)
-    (-> the CURRENT values, i.e. after an EM update, as compute_SMC_loss sees them — train_step_functions.py:43-54)."""
+    (-> the CURRENT values, i.e. after an EM update, as compute_SMC_loss sees them — train_step_functions.py:43-54).
+    classic_w (B,S): weight of the classic-loss term of every row relative to the uniform mean (masked losses)."""
     m = smc_transformer
     fwd = m._last_forward
     if fwd is None:
@@ -28,7 +29,7 @@ def compute_gradients(smc_transformer, inputs, targets, inv_n=None, loss_variant
     if snap is not None:
         params["logvar_q"], params["logvar_z"] = snap["logvar_q"], snap["logvar_z"]
     return F.backward(fwd["shape"], params, fwd["x"], fwd["y"], fwd["out"], eps=fwd["eps"], seed=fwd["seed"],
-                      inv_n=inv_n, loss_variant=loss_variant)
+                      inv_n=inv_n, loss_variant=loss_variant, classic_w=classic_w)
 
 
 def _is_regression(targets):
@@ -53,7 +54,7 @@ def train_step_SMC_T(inputs, targets, smc_transformer, optimizer, it, attention_
                                                               attention_mask=attention_mask)
     loss = smc_loss
     if regression:
-        metric = compute_mse_metric(targets, preds)
+        metric = compute_mse_metric(targets, preds, attention_mask=attention_mask)
     else:
         metric = compute_categorical_cross_entropy(targets=targets, preds=preds,
                                                    num_particles=smc_transformer.cell.num_particles,
@@ -62,8 +63,14 @@ def train_step_SMC_T(inputs, targets, smc_transformer, optimizer, it, attention_
         rank, world = D.world()
         B, P, S = preds.shape[0], preds.shape[1], preds.shape[2]
         # regression era (pyc): no log-determinant terms; the nlp checkout: full -log N terms + sparse cross-entropy
+        classic_w = None
+        mask = smc_transformer._last_mask
+        if mask is not None:   # masked mean of compute_classic_loss: mask[b,s] * (global B*S) / (global sum of the mask)
+            tot = mask.sum(dtype=torch.float64).reshape(1)
+            D.allreduce_sums(tot)
+            classic_w = (mask * (float(B) * world * S / float(tot.item()))).contiguous()
         grads = compute_gradients(smc_transformer, inputs, targets, inv_n=1.0 / (float(B) * world * P * S),
-                                  loss_variant="pyc" if regression else "checkout")
+                                  loss_variant="pyc" if regression else "checkout", classic_w=classic_w)
         params = smc_transformer._last_forward["params"]
         # optimizer.apply_gradients(zip(gradients, trainable_variables)): only TRAINABLE variables are updated — in EM
         # mode the log-variances are plain tensors outside trainable_variables (self_attention_SMC.py:48-52)

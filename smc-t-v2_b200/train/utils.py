@@ -9,19 +9,28 @@ from ..models.SMC_Transformer.self_attention_SMC import logvar_vector
 
 
 def compute_categorical_cross_entropy(targets, preds, num_particles, attention_mask=None):
-    """train/utils.py:3-20: sparse CE of the particle-mean softmax (classification era)."""
-    if attention_mask is not None:
-        raise NotImplementedError("masked metric is out of scope")
+    """train/utils.py:3-20: sparse CE of the particle-mean softmax (classification era); masked mean with an
+    attention_mask (:15-19).  A metric on tensors the forward already produced — small host-side bookkeeping."""
     probs = torch.softmax(preds, dim=-1).mean(dim=1, keepdim=True)              # (B,1,S,V)
     B, _, S, V = probs.shape
     t = torch.as_tensor(targets).reshape(B, 1, S, 1).to(probs.device, torch.int64)
-    return -(torch.log(torch.gather(probs, -1, t).clamp_min(1e-7))).mean()
+    ce = -(torch.log(torch.gather(probs, -1, t).clamp_min(1e-7))).reshape(B, S)
+    if attention_mask is None:
+        return ce.mean()
+    m = torch.as_tensor(attention_mask).to(ce.device, torch.float32).reshape(B, S)
+    # the reference tiles the mask over the particles but the loss has one particle-mean row per (b,s): (B,1,S) * (B,P,S)
+    # broadcasts, so numerator and denominator both carry the factor P
+    return (ce * m).sum() / m.sum()
 
 
-def compute_mse_metric(targets, preds):
+def compute_mse_metric(targets, preds, attention_mask=None):
     """Regression-era metric (pyc train_step_SMC_T): MSE of the particle-mean prediction."""
     t = torch.as_tensor(targets).to(preds.device, torch.float32)
-    return (preds.mean(dim=1, keepdim=True) - t).square().mean()
+    se = (preds.mean(dim=1, keepdim=True) - t).square()
+    if attention_mask is None:
+        return se.mean()
+    m = torch.as_tensor(attention_mask).to(preds.device, torch.float32).reshape(se.shape[0], 1, se.shape[2], 1)
+    return (se * m).sum() / (m.sum() * se.shape[-1])
 
 
 def EM_update(err, logvar, it, EM_param):

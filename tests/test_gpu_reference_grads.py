@@ -26,6 +26,10 @@ def test_backward_matches_reference_tape_gradient(path):
     dp = util.dev_params(p)
     tx, ty = torch.as_tensor(x_in, device="cuda"), torch.as_tensor(y, device="cuda")
     te, tu = torch.as_tensor(g["eps"], device="cuda"), torch.as_tensor(g["u"], device="cuda")
+    classic_w = None
+    if "mask" in g.files:   # attention_mask: weight of the classic-loss term of row (b,s) relative to the uniform mean
+        m = g["mask"].reshape(cfg.B, cfg.S).astype(np.float32)
+        classic_w = torch.as_tensor(m * (cfg.B * cfg.S / m.sum()), device="cuda").contiguous()
     for algo in _algos(cfg):
         ld = util.logvar_dim(p)    # 1, or d_model for the noise_dim = "multi" fixtures
         shape = F.shape_from_config(cfg, logvar_dim=ld, algo=algo)
@@ -33,7 +37,7 @@ def test_backward_matches_reference_tape_gradient(path):
         fwd = F.forward(shape, dp, tx, ty, te, tu, want=want)
         # the forward is the one the reference ran: same resampled predictions
         util.assert_close(name + ":pred_resampl", fwd["pred_resampl"].cpu().numpy(), g["pred_resampl"])
-        grads = F.backward(shape, dp, tx, ty, fwd, eps=te, loss_variant=variant)
+        grads = F.backward(shape, dp, tx, ty, fwd, eps=te, loss_variant=variant, classic_w=classic_w)
         torch.cuda.synchronize()
         got = {k: v.cpu().numpy() for k, v in grads.items()}
         worst = RG.compare_grads(name + ":" + algo, got, ref)
@@ -82,7 +86,8 @@ def test_mirror_loss_matches_reference(path):
     else:
         model.projection_layer_ts.build(cfg.F_x, np.random.default_rng(0))
         model.projection_layer_ts.kernel.assign(p["W_in"]); model.projection_layer_ts.bias.assign(p["b_in"])
-    (_, pred_r), _, _ = model(inputs, targets, eps=g["eps"], u=g["u"])
-    total, classic = model.compute_SMC_loss(inputs=inputs, targets=targets, predictions=pred_r)
+    mask = torch.from_numpy(g["mask"]) if "mask" in g.files else None
+    (_, pred_r), _, _ = model(inputs, targets, attention_mask=mask, eps=g["eps"], u=g["u"])
+    total, classic = model.compute_SMC_loss(inputs=inputs, targets=targets, predictions=pred_r, attention_mask=mask)
     assert np.isclose(float(total), float(g["loss_total"]), rtol=2e-4), (float(total), float(g["loss_total"]))
     assert np.isclose(float(classic), float(g["loss_classic"]), rtol=2e-4)

@@ -201,3 +201,33 @@ def test_train_per_dimension_variances():
     off = ~np.eye(8, dtype=bool)
     assert np.array_equal(lv1[off], lv0[off]) and np.all(np.diagonal(lv1) != np.diagonal(lv0))
     assert np.all(np.isfinite(losses)) and losses[-1] < losses[0], losses
+
+
+def test_train_step_with_attention_mask():
+    """(inputs, targets, attention_mask) batches of the NLP datasets: the mask weights the classic loss, its gradient and
+    the metric (SMC_Transformer.py:158-163, train/utils.py:15-19); a fully padded-out row gets no classic-loss gradient."""
+    from smct_b200.algos.run_SMC_T import SMCTAlgo, default_args
+    from smct_b200.train.optimizers import Adam
+    from smct_b200.train.train_step_functions import compute_gradients, train_step_SMC_T
+    ds = TinyDataset(classification=True, n_train=1, n_val=1)
+    algo = SMCTAlgo(dataset=ds, args=default_args(d_model=16, dff=16, particles=6, sigmas=0.1, ep=1, bs=8))
+    m = algo.smc_transformer
+    m.noise_z_mode, m.seed = "pyc", 5
+    inp, tar, _ = algo.train_dataset[0]
+    B, S = inp.shape[0], inp.shape[2]
+    mask = np.ones((B, 1, S, 1), np.int32)
+    mask[:, :, S - 3:, :] = 0
+    loss_m, metric_m = train_step_SMC_T(inp, tar, m, None, it=1, attention_mask=mask)
+    loss_u, metric_u = train_step_SMC_T(inp, tar, m, None, it=1)
+    assert np.isfinite(float(loss_m)) and float(loss_m) != float(loss_u) and float(metric_m) != float(metric_u)
+    # classic loss by hand from the returned logits
+    (pred, pred_r), _, _ = m(inp, tar, attention_mask=mask)
+    lp = torch.log_softmax(pred_r.double(), -1)
+    y = torch.as_tensor(tar).reshape(B, 1, S, 1).to(lp.device, torch.int64).expand(B, pred_r.shape[1], S, 1)
+    ce = -torch.gather(lp, -1, y).squeeze(-1)
+    mm = torch.as_tensor(mask, device=lp.device).double().reshape(B, 1, S)
+    want = float((ce * mm).sum() / (mm.sum() * pred_r.shape[1]))
+    assert abs(float(m.compute_classic_loss(tar, pred_r, attention_mask=mask)) - want) < 1e-5 * abs(want)
+    opt = Adam(1e-2)
+    losses = [float(train_step_SMC_T(inp, tar, m, opt, it=i + 1, attention_mask=mask)[0]) for i in range(5)]
+    assert np.all(np.isfinite(losses)) and losses[-1] < losses[0], losses

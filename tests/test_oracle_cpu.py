@@ -191,11 +191,12 @@ def test_gradient_oracle_matches_reference_tape_gradient():
     from oracle import ref_eager_torch as E
     from tests import ref_grad_golden as RG
     paths = RG.files()
-    assert len(paths) >= 4
+    assert len(paths) >= 7
     for path in paths:
         g, cfg, p, ref, x_in, y, variant = RG.load(path)
         ora = O.forward(cfg, p, x_in, y, g["eps"], g["u"])
-        _, grads = E.loss_and_grads(cfg, p, x_in, y, g["eps"], ora["i_t"], variant=variant)
+        mask = g["mask"] if "mask" in g.files else None
+        _, grads = E.loss_and_grads(cfg, p, x_in, y, g["eps"], ora["i_t"], variant=variant, mask=mask)
         RG.compare_grads(path, grads, ref)
 
 
