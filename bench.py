@@ -14,6 +14,7 @@ a sequence live on one GPU).  Prints ONE JSON line on rank 0.  Besides the contr
   train         configs[4]: one optimiser step (forward + smct_backward + NCCL gradient all-reduce + Adam) on a
                 resident shard per GPU, the all-reduce inside the timed region
   e2e           host buffers in, pred / pred_resampl / w back in pinned host memory (and a loss-only variant)
+  strong_scaling (N > 1) the same 4096 global sequences split over the ranks
 """
 import argparse
 import ctypes
@@ -475,6 +476,37 @@ def run_b200(args):
     value = psteps_per_gpu * world / (total_ms_max * 1e-3)
     loss_dev = loss_from_sums(loss_sums.cpu())
 
+    # ---------------- strong scaling: the SAME global batch split over the ranks (N > 1 only) ----------------
+    strong = None
+    if world > 1 and wl == "c4" and not args.no_extras and not args.batch:
+        from smct_b200.distributed import shard_range
+        g0, g1 = shard_range(B, rank, world)            # this rank's contiguous shard of the 4096 global sequences
+        Bs = g1 - g0
+
+        def forward_shard(seed):
+            for c0 in range(0, Bs, chunk):
+                n = min(chunk, Bs - c0)
+                shape = F_.make_shape(n, P, S, D, dff=dff, F_x=F, F_y=F, algo=args.algo, b_global0=g0 + c0, sigma_obs=args.sigma_obs)
+                out = dict(pred=pred[c0:c0 + n], pred_resampl=pred_r[c0:c0 + n], w=w[c0:c0 + n], K=Kc[:n], V=Vc[:n], R=Rc[:n],
+                           loss_sums=loss_sums[0])
+                F_.forward(shape, params, x_dev[c0:c0 + n], y_dev[c0:c0 + n], seed=seed, want=("loss_sums",), out=out)
+        forward_shard(400)
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s_steps = 2
+        s0.record()
+        for i in range(s_steps):
+            forward_shard(401 + i)
+        s1.record()
+        barrier()
+        ts = torch.tensor([s0.elapsed_time(s1) / s_steps], dtype=torch.float64, device=dev)
+        dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+        waves = -(-Bs // (wave or n_sm))
+        strong = {"global_batch": B, "per_gpu_batch": Bs, "ms_per_step": float(ts.item()), "value": float(B) * P * S / (float(ts.item()) * 1e-3),
+                  "unit": UNIT, "steps": s_steps, "scaling": "strong",
+                  "waves_per_gpu": "%d sequences = %d wave(s) of %d resident sequences (the last one %s)" % (
+                      Bs, waves, wave or n_sm, "full" if Bs % (wave or n_sm) == 0 else "partial: %d" % (Bs % (wave or n_sm)))}
+
     # ---------------- end-to-end through the public API with HOST buffers ----------------
     # (a) "outputs": what SMC_Transformer.call hands its caller that fits a host — pred, pred_resampl (B,P,S,F) and the
     #     filtering weights w (B,P,S) — lands in pinned host memory, chunk by chunk on a copy stream, plus the loss sums;
@@ -577,6 +609,7 @@ def run_b200(args):
             "loss": loss_dev,
             "other_shapes": other_shapes,
             "train": train,
+            "strong_scaling": strong,
         }
         print(json.dumps(line), flush=True)
     if dist is not None:
