@@ -229,6 +229,13 @@ int smct_tc_selftest(const float *A, const float *W, float *D, void *scratch, vo
 int smct_classic_loss(int32_t B, int32_t P, int32_t S, int32_t F_y, int32_t weights_mode, const float *pred,
                       const void *y, const float *mask, double *out, void *stream);
 
+/* The training metric of train_step_SMC_T on the unresampled predictions pred (B,P,S,F_y):
+ * classification — compute_categorical_cross_entropy, src/train/utils.py:3-20: sparse CE of the particle-mean softmax;
+ * gaussian — regression era (pyc): squared error of the particle-mean prediction, summed over F_y.
+ * out[0] += sum_{b,s} m[b,s] * metric[b,s], out[1] += sum_{b,s} m[b,s]; mask (B,S) f32 or NULL (:15-19). */
+int smct_metric(int32_t B, int32_t P, int32_t S, int32_t F_y, int32_t weights_mode, const float *pred, const void *y,
+                const float *mask, double *out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -86,6 +86,7 @@ def _declare(lib):
         "smct_tc_selftest": (ctypes.c_int, [VP, VP, VP, VP, VP]),
         "smct_encode": (ctypes.c_int, [SP, PP, VP, VP, VP, VP]),
         "smct_classic_loss": (ctypes.c_int, [i32, i32, i32, i32, i32, VP, VP, VP, VP, VP]),
+        "smct_metric": (ctypes.c_int, [i32, i32, i32, i32, i32, VP, VP, VP, VP, VP]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)  # AttributeError if the symbol is missing: loud by design

@@ -942,4 +942,14 @@ int smct_classic_loss(int32_t B, int32_t P, int32_t S, int32_t F_y, int32_t weig
   return SMCT_OK;
 }
 
+int smct_metric(int32_t B, int32_t P, int32_t S, int32_t F_y, int32_t weights_mode, const float* pred, const void* y,
+                const float* mask, double* out, void* stream) {
+  if (B < 1 || P < 1 || S < 1 || F_y < 1 || !pred || !y || !out) return fail(SMCT_ERR_INVALID, "smct_metric: bad arguments");
+  const long long rows = (long long)B * S;
+  smct::metric_kernel<<<(int)std::min<long long>((rows + 7) / 8, 148 * 8), 256, 0, (cudaStream_t)stream>>>(
+      B, P, S, F_y, weights_mode, pred, y, mask, out);
+  SMCT_LAUNCH_CHECK("metric_kernel");
+  return SMCT_OK;
+}
+
 }  // extern "C"

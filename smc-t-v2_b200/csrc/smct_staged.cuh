@@ -773,6 +773,56 @@ __global__ void __launch_bounds__(256) final_kernel(const FinalArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------
+// metric_kernel: the training metric of train_step_SMC_T on the UNRESAMPLED predictions (B,P,S,Fy), one warp per (b,s):
+//   classification (train/utils.py:3-20): -log( mean_p softmax(pred[b,p,s,:])[y[b,s]] ), floored at 1e-7 like Keras'
+//   SparseCategoricalCrossentropy on probabilities;  regression (pyc): sum_f (mean_p pred[b,p,s,f] - y[b,s,f])^2.
+// out[0] += sum_{b,s} m[b,s] * metric, out[1] += sum_{b,s} m[b,s]  (mask (B,S) optional).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) metric_kernel(int B, int P, int S, int Fy, int mode, const float* pred, const void* y,
+                                                     const float* mask, double* out) {
+  __shared__ double red[2][8];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  double acc = 0.0, cnt = 0.0;
+  for (long long bs = (long long)blockIdx.x * 8 + wid; bs < (long long)B * S; bs += (long long)gridDim.x * 8) {
+    const int b = (int)(bs / S), s = (int)(bs % S);
+    const float mk = mask ? mask[bs] : 1.f;
+    float val = 0.f;
+    if (mode == SMCT_WEIGHTS_CLASSIFICATION) {
+      const int tgt = clamp_index(((const int*)y)[bs], Fy);
+      float psum = 0.f;                                   // sum over particles of softmax(...)[tgt]
+      for (int p = 0; p < P; ++p) {
+        const float* pr = pred + (((long long)b * P + p) * S + s) * Fy;
+        float mx = -INFINITY;
+        for (int f = lane; f < Fy; f += 32) mx = fmaxf(mx, pr[f]);
+        mx = warp_max(mx);
+        float se = 0.f;
+        for (int f = lane; f < Fy; f += 32) se += expf(pr[f] - mx);
+        se = warp_sum(se);
+        psum += expf(pr[tgt] - mx) / se;
+      }
+      val = -logf(fmaxf(psum / (float)P, 1e-7f));
+    } else {
+      for (int f = 0; f < Fy; ++f) {
+        float part = 0.f;
+        for (int p = lane; p < P; p += 32) part += pred[(((long long)b * P + p) * S + s) * Fy + f];
+        const float d = warp_sum(part) / (float)P - ((const float*)y)[bs * Fy + f];
+        val = fmaf(d, d, val);
+      }
+    }
+    acc += (double)val * (double)mk;
+    cnt += (double)mk;
+  }
+  if (lane == 0) { red[0][wid] = acc; red[1][wid] = cnt; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a0 = 0, a1 = 0;
+    for (int i = 0; i < 8; ++i) { a0 += red[0][i]; a1 += red[1][i]; }
+    atomicAdd(out, a0);
+    atomicAdd(out + 1, a1);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // small utility kernels
 // ------------------------------------------------------------------------------------------
 __global__ void fill_noise_kernel(unsigned long long seed, int which, int t, long long b0, int B, int P, int D,

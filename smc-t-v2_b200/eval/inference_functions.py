@@ -61,7 +61,6 @@ def inference_multistep(smc_transformer, inputs, targets, past_len=40, future_le
     enc_shape = F.make_shape(B, 1, past_len, D, F_x=Fx, F_y=Fy, input_mode="linear", dff=m.dff)
     X_past = F.encode(enc_shape, params, inputs[:, 0, :past_len].contiguous())                  # (B,past_len,D)
     preds = []
-    gen = torch.Generator(device=dev).manual_seed(int(seed))
     x_next = None
     cvt = lambda a, dt: None if a is None else torch.as_tensor(np.asarray(a), device=dev).to(dt).contiguous()
     eps, u, obs_noise = cvt(eps, torch.float32), cvt(u, torch.float64), cvt(obs_noise, torch.float32)
@@ -77,7 +76,8 @@ def inference_multistep(smc_transformer, inputs, targets, past_len=40, future_le
             st = F.cell_step(shape, params, t, X_t, dummy_y, K, V, R, seed=seed, want_attn=False, **inj)
             preds.append(st["pred"])
         # next input of every particle: its own prediction plus observation noise
-        n_obs = torch.randn(st["pred"].shape, device=dev, generator=gen) if obs_noise is None else obs_noise[t]
+        # observation noise from the library's own generator (stream 0 of a derived seed; (B,P,F_y) normals)
+        n_obs = F.fill_noise(int(seed) ^ 0x0B5E, 0, t, 0, B, P, Fy, device=dev) if obs_noise is None else obs_noise[t]
         x_next = st["pred"] + math.sqrt(c.Sigma_obs) * n_obs
     preds_future = torch.stack(preds, dim=2)                                                     # (B,P,future_len,F_y)
     return preds_future, preds_future.mean(dim=1)

@@ -332,6 +332,21 @@ def classic_loss_sum(pred: torch.Tensor, y: torch.Tensor, weights="gaussian", ma
     return out
 
 
+def metric_sums(pred: torch.Tensor, y: torch.Tensor, weights="gaussian", mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """(sum_{b,s} m*metric, sum_{b,s} m) of the training metric on the unresampled predictions (B,P,S,Fy): sparse CE of
+    the particle-mean softmax (classification) or squared error of the particle-mean prediction (gaussian); fp64 (2,)."""
+    require_cuda()
+    lib = _lib.load()
+    B, P, S, Fy = pred.shape
+    out = torch.zeros((2,), dtype=torch.float64, device=pred.device)
+    y_dtype = torch.int32 if weights == "classification" else torch.float32
+    if mask is not None and tuple(mask.shape) != (B, S):
+        raise ValueError("mask must have shape (B,S)")
+    check(lib.smct_metric(B, P, S, Fy, WEIGHTS[weights], _ptr(pred, torch.float32, "pred"), _ptr(y, y_dtype, "y"),
+                          _ptr(mask, torch.float32, "mask"), _ptr(out), _stream()))
+    return out
+
+
 def encode(shape: SmctShape, params, x_in: torch.Tensor, layer_norm=False) -> torch.Tensor:
     """get_encoded_input: (B,S,D) encoded rows (optionally after layernorm1), shared by the particles."""
     require_cuda()

@@ -8,29 +8,30 @@ from .. import functional as F
 from ..models.SMC_Transformer.self_attention_SMC import logvar_vector
 
 
-def compute_categorical_cross_entropy(targets, preds, num_particles, attention_mask=None):
-    """train/utils.py:3-20: sparse CE of the particle-mean softmax (classification era); masked mean with an
-    attention_mask (:15-19).  A metric on tensors the forward already produced — small host-side bookkeeping."""
-    probs = torch.softmax(preds, dim=-1).mean(dim=1, keepdim=True)              # (B,1,S,V)
-    B, _, S, V = probs.shape
-    t = torch.as_tensor(targets).reshape(B, 1, S, 1).to(probs.device, torch.int64)
-    ce = -(torch.log(torch.gather(probs, -1, t).clamp_min(1e-7))).reshape(B, S)
+def _mask_bs(attention_mask, B, S, device):
     if attention_mask is None:
-        return ce.mean()
-    m = torch.as_tensor(attention_mask).to(ce.device, torch.float32).reshape(B, S)
-    # the reference tiles the mask over the particles but the loss has one particle-mean row per (b,s): (B,1,S) * (B,P,S)
-    # broadcasts, so numerator and denominator both carry the factor P
-    return (ce * m).sum() / m.sum()
+        return None
+    return torch.as_tensor(attention_mask).to(device, torch.float32).reshape(B, S).contiguous()
+
+
+def compute_categorical_cross_entropy(targets, preds, num_particles, attention_mask=None):
+    """train/utils.py:3-20: sparse CE of the particle-mean softmax (classification era), masked mean with an
+    attention_mask (:15-19; the mask is tiled over the particles there but the loss has one row per (b,s), so numerator
+    and denominator both carry the factor P).  Computed by smct_metric (C-ABI)."""
+    preds = preds.to(torch.float32).contiguous()
+    B, P, S, V = preds.shape
+    y = torch.as_tensor(targets).reshape(B, S).to(preds.device, torch.int32).contiguous()
+    sums = F.metric_sums(preds, y, "classification", mask=_mask_bs(attention_mask, B, S, preds.device))
+    return sums[0] / sums[1]
 
 
 def compute_mse_metric(targets, preds, attention_mask=None):
-    """Regression-era metric (pyc train_step_SMC_T): MSE of the particle-mean prediction."""
-    t = torch.as_tensor(targets).to(preds.device, torch.float32)
-    se = (preds.mean(dim=1, keepdim=True) - t).square()
-    if attention_mask is None:
-        return se.mean()
-    m = torch.as_tensor(attention_mask).to(preds.device, torch.float32).reshape(se.shape[0], 1, se.shape[2], 1)
-    return (se * m).sum() / (m.sum() * se.shape[-1])
+    """Regression-era metric (pyc train_step_SMC_T): MSE of the particle-mean prediction.  Computed by smct_metric."""
+    preds = preds.to(torch.float32).contiguous()
+    B, P, S, Fy = preds.shape
+    y = torch.as_tensor(targets).to(preds.device, torch.float32).reshape(B, S, Fy).contiguous()
+    sums = F.metric_sums(preds, y, "gaussian", mask=_mask_bs(attention_mask, B, S, preds.device))
+    return sums[0] / (sums[1] * Fy)
 
 
 def EM_update(err, logvar, it, EM_param):

@@ -231,3 +231,30 @@ def test_train_step_with_attention_mask():
     opt = Adam(1e-2)
     losses = [float(train_step_SMC_T(inp, tar, m, opt, it=i + 1, attention_mask=mask)[0]) for i in range(5)]
     assert np.all(np.isfinite(losses)) and losses[-1] < losses[0], losses
+
+
+@pytest.mark.parametrize("masked", [False, True])
+def test_metric_kernel_matches_torch(masked):
+    """smct_metric (the training metric, src/train/utils.py:3-20 / the regression-era MSE of the particle mean) against a
+    torch fp64 restatement."""
+    from smct_b200.train.utils import compute_categorical_cross_entropy, compute_mse_metric
+    rng = np.random.default_rng(3)
+    B, P, S, V = 5, 7, 9, 33
+    mask = (rng.random((B, 1, S, 1)) > 0.3).astype(np.int32) if masked else None
+    m = None if mask is None else torch.as_tensor(mask).double().reshape(B, S)
+    # classification
+    pred = torch.as_tensor(rng.standard_normal((B, P, S, V)).astype(np.float32) * 3, device="cuda")
+    tar = rng.integers(0, V, size=(B, 1, S, 1)).astype(np.int32)
+    got = float(compute_categorical_cross_entropy(tar, pred, P, attention_mask=mask))
+    probs = torch.softmax(pred.double().cpu(), -1).mean(1)                                    # (B,S,V)
+    ce = -torch.log(torch.gather(probs, -1, torch.as_tensor(tar).long().reshape(B, S, 1)).squeeze(-1).clamp_min(1e-7))
+    want = float(ce.mean()) if m is None else float((ce * m).sum() / m.sum())
+    assert abs(got - want) < 1e-5 * abs(want), (got, want)
+    # regression
+    Fy = 3
+    pred = torch.as_tensor(rng.standard_normal((B, P, S, Fy)).astype(np.float32), device="cuda")
+    tar = rng.standard_normal((B, 1, S, Fy)).astype(np.float32)
+    got = float(compute_mse_metric(tar, pred, attention_mask=mask))
+    se = (pred.double().cpu().mean(1) - torch.as_tensor(tar).double().reshape(B, S, Fy)).square()
+    want = float(se.mean()) if m is None else float((se * m.unsqueeze(-1)).sum() / (m.sum() * Fy))
+    assert abs(got - want) < 1e-5 * abs(want), (got, want)
