@@ -519,8 +519,13 @@ int launch_backward_t(const smct::BwdArgs& a, cudaStream_t st) {
   const long long ntiles = (nrows + smct::PT - 1) / smct::PT;
   smct::bwd_dense_kernel<KD><<<(int)std::min<long long>(ntiles, a.nrep), smct::NT, smem_d, st>>>(a);
   SMCT_LAUNCH_CHECK("bwd_dense_kernel");
-  smct::bwd_attn_bwd_kernel<KD><<<a.B * smct::BWD_G, smct::BWD_ANT, 0, st>>>(a);
-  SMCT_LAUNCH_CHECK("bwd_attn_bwd_kernel");
+  if (D % 4 == 0 && D <= 64) {   // rows as one float4 per lane of a half-warp: two target slots per warp at a time
+    smct::bwd_attn_bwd_half_kernel<1><<<a.B * smct::BWD_G, smct::BWD_ANT, 0, st>>>(a);   // (<2>, d_model 128, spills at 128 registers)
+    SMCT_LAUNCH_CHECK("bwd_attn_bwd_half_kernel");
+  } else {
+    smct::bwd_attn_bwd_kernel<KD><<<a.B * smct::BWD_G, smct::BWD_ANT, 0, st>>>(a);
+    SMCT_LAUNCH_CHECK("bwd_attn_bwd_kernel");
+  }
   return SMCT_OK;
 }
 
