@@ -171,6 +171,12 @@ __global__ void transpose_kernel(const float* in, float* out, int rows, int cols
   }
 }
 
+__device__ __forceinline__ float half_sum(float v) {   // sum over the 16 lanes of a half-warp (all 32 lanes participate)
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(SMCT_FULL_MASK, v, o);
+  return v;
+}
+
 __device__ __forceinline__ float bwd_eps(const BwdArgs& a, int which, int b, int s, int L, int d) {
   if (a.eps) return a.eps[((((long long)which * a.S + s) * a.B + b) * a.P + L) * a.D + d];
   const unsigned long long gbp = (unsigned long long)(a.b_global0 + b) * (unsigned long long)a.P + L;
@@ -229,6 +235,77 @@ __global__ void __launch_bounds__(256) bwd_attn_fwd_kernel(const BwdArgs a) {
       if (d < D) { a.Zm[u * D + d] = acc[k] / l; a.Qm[u * D + d] = q[k]; }
     }
     if (lane == 0) { a.stat[u * 2] = m; a.stat[u * 2 + 1] = l; }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// attention forward recompute, half-warp form (d_model a multiple of 4, <= 64): one warp per node; a row is one float4
+// per lane of a half-warp, the two halves take alternate slots with their own running (max, sum, z) and merge at the end
+// (half the dependent online-softmax steps per node, 4-step reductions, 128-bit loads).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) bwd_attn_fwd_half_kernel(const BwdArgs a) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int l16 = lane & 15, hsel = lane >> 4;
+  const int D = a.D, S = a.S;
+  const long long nnodes = a.node_off[a.B * S];
+  const bool multi = a.logvar_dim > 1;
+  const int d0 = 4 * l16;
+  const bool okd = d0 < D;
+  float std_q[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) std_q[e] = expf(0.5f * a.p.logvar_q[(multi && okd) ? d0 + e : 0]);
+  const float inv_sqrt_d = 1.0f / sqrtf((float)D);
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (long long u = (long long)blockIdx.x * 8 + wid; u < nnodes; u += (long long)gridDim.x * 8) {
+    const int bs = a.node_bs[u];
+    const int s = bs % S, b = bs / S;
+    const long long bp = (long long)b * a.P + a.node_p[u];
+    const int L = a.node_L[u];
+    const int s_lo = (a.attn_window >= 0 && s > a.attn_window) ? s - a.attn_window : 0;
+    float4 q = zero4;
+    if (okd) {
+      const float4 qb = *reinterpret_cast<const float4*>(a.q_ + (long long)bs * D + d0);
+      q.x = __fadd_rn(qb.x, __fmul_rn(std_q[0], bwd_eps(a, 1, b, s, L, d0)));
+      q.y = __fadd_rn(qb.y, __fmul_rn(std_q[1], bwd_eps(a, 1, b, s, L, d0 + 1)));
+      q.z = __fadd_rn(qb.z, __fmul_rn(std_q[2], bwd_eps(a, 1, b, s, L, d0 + 2)));
+      q.w = __fadd_rn(qb.w, __fmul_rn(std_q[3], bwd_eps(a, 1, b, s, L, d0 + 3)));
+    }
+    const float* Kp = a.K + bp * S * D;
+    const float* Vp = a.V + bp * S * D;
+    float m = -INFINITY, l = 0.f;
+    float4 acc = zero4;
+    for (int tb = s_lo; tb <= s; tb += 2) {
+      const int t = tb + hsel;
+      const bool valid = t <= s;                      // uniform per half-warp; all lanes execute the shuffles
+      const float4 kv = (valid && okd) ? *reinterpret_cast<const float4*>(Kp + (long long)t * D + d0) : zero4;
+      const float4 vr = (valid && okd) ? *reinterpret_cast<const float4*>(Vp + (long long)t * D + d0) : zero4;
+      const float sc = half_sum(fmaf(q.x, kv.x, fmaf(q.y, kv.y, fmaf(q.z, kv.z, q.w * kv.w)))) * inv_sqrt_d;
+      if (valid) {
+        const float mn = fmaxf(m, sc);
+        const float corr = expf(m - mn), pj = expf(sc - mn);
+        l = l * corr + pj;
+        acc.x = fmaf(pj, vr.x, acc.x * corr); acc.y = fmaf(pj, vr.y, acc.y * corr);
+        acc.z = fmaf(pj, vr.z, acc.z * corr); acc.w = fmaf(pj, vr.w, acc.w * corr);
+        m = mn;
+      }
+    }
+    // merge the two halves (the upper one may be empty: m = -inf, l = 0)
+    const float mo = __shfl_xor_sync(SMCT_FULL_MASK, m, 16), lo = __shfl_xor_sync(SMCT_FULL_MASK, l, 16);
+    const float4 ao = make_float4(__shfl_xor_sync(SMCT_FULL_MASK, acc.x, 16), __shfl_xor_sync(SMCT_FULL_MASK, acc.y, 16),
+                                  __shfl_xor_sync(SMCT_FULL_MASK, acc.z, 16), __shfl_xor_sync(SMCT_FULL_MASK, acc.w, 16));
+    const float mt = fmaxf(m, mo);
+    const float ca = expf(m - mt), cb = (mo == -INFINITY) ? 0.f : expf(mo - mt);
+    // both halves form the same totals in the same order (lower half's terms first)
+    const float l_lo = hsel ? lo : l, l_hi = hsel ? l : lo, c_lo = hsel ? cb : ca, c_hi = hsel ? ca : cb;
+    const float lt = l_lo * c_lo + l_hi * c_hi;
+    const float4 a_lo = hsel ? ao : acc, a_hi = hsel ? acc : ao;
+    if (hsel == 0 && okd) {
+      const float inv_l = 1.0f / lt;
+      *reinterpret_cast<float4*>(a.Zm + u * D + d0) = make_float4((a_lo.x * c_lo + a_hi.x * c_hi) * inv_l, (a_lo.y * c_lo + a_hi.y * c_hi) * inv_l,
+                                                                  (a_lo.z * c_lo + a_hi.z * c_hi) * inv_l, (a_lo.w * c_lo + a_hi.w * c_hi) * inv_l);
+      *reinterpret_cast<float4*>(a.Qm + u * D + d0) = q;
+    }
+    if (lane == 0) { a.stat[u * 2] = mt; a.stat[u * 2 + 1] = lt; }
   }
 }
 
@@ -615,12 +692,6 @@ __global__ void __launch_bounds__(BWD_ANT) bwd_attn_bwd_kernel(const BwdArgs a) 
 // their dk / dv sums in registers.  The warp-sum form above cost 2 x (5 shuffles + 5 adds) of ~45 instructions per pair.
 // ------------------------------------------------------------------------------------------
 constexpr int BWD_TJ2 = 4;      // target slots per half-warp and pass (16 warps x 2 halves x 4 = 128 slots per pass)
-
-__device__ __forceinline__ float half_sum(float v) {   // sum over the 16 lanes of a half-warp (all 32 lanes participate)
-#pragma unroll
-  for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(SMCT_FULL_MASK, v, o);
-  return v;
-}
 
 template <int K4>
 __global__ void __launch_bounds__(BWD_ANT) bwd_attn_bwd_half_kernel(const BwdArgs a) {
