@@ -236,6 +236,14 @@ int smct_classic_loss(int32_t B, int32_t P, int32_t S, int32_t F_y, int32_t weig
 int smct_metric(int32_t B, int32_t P, int32_t S, int32_t F_y, int32_t weights_mode, const float *pred, const void *y,
                 const float *mask, double *out, void *stream);
 
+/* EM(smc_transformer, it, EM_param) — src/train/utils.py:22-51: per batch element j (in order) every scalar
+ * log-variance is replaced by log((1 - it^-a) exp(logvar) + it^-a mean(noise[j]^2)) (EM_update, :48-51), for the four
+ * recorded noises noise_K_resampled, noise_q, noise_V_resampled, noise_z, each (B, per_b) with per_b = P*S*D.
+ * The log-variances (device scalars) are updated in place; scratch: >= 4*B doubles of device memory. */
+int smct_em_update(int32_t B, int64_t per_b, const float *noise_k, const float *noise_q, const float *noise_v,
+                   const float *noise_z, float *logvar_k, float *logvar_q, float *logvar_v, float *logvar_z, float it,
+                   float em_param, void *scratch, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -87,6 +87,7 @@ def _declare(lib):
         "smct_encode": (ctypes.c_int, [SP, PP, VP, VP, VP, VP]),
         "smct_classic_loss": (ctypes.c_int, [i32, i32, i32, i32, i32, VP, VP, VP, VP, VP]),
         "smct_metric": (ctypes.c_int, [i32, i32, i32, i32, i32, VP, VP, VP, VP, VP]),
+        "smct_em_update": (ctypes.c_int, [i32, i64, VP, VP, VP, VP, VP, VP, VP, VP, f32, f32, VP, VP]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)  # AttributeError if the symbol is missing: loud by design

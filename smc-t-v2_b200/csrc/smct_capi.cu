@@ -958,4 +958,18 @@ int smct_metric(int32_t B, int32_t P, int32_t S, int32_t F_y, int32_t weights_mo
   return SMCT_OK;
 }
 
+int smct_em_update(int32_t B, int64_t per_b, const float* noise_k, const float* noise_q, const float* noise_v,
+                   const float* noise_z, float* logvar_k, float* logvar_q, float* logvar_v, float* logvar_z, float it,
+                   float em_param, void* scratch, void* stream) {
+  if (B < 1 || per_b < 1 || !noise_k || !noise_q || !noise_v || !noise_z || !logvar_k || !logvar_q || !logvar_v || !logvar_z || !scratch)
+    return fail(SMCT_ERR_INVALID, "smct_em_update: bad arguments");
+  if (!(it > 0.f)) return fail(SMCT_ERR_INVALID, "smct_em_update: it must be > 0");
+  cudaStream_t st = (cudaStream_t)stream;
+  smct::em_err_kernel<<<4 * B, 256, 0, st>>>(B, per_b, noise_k, noise_q, noise_v, noise_z, (double*)scratch);
+  SMCT_LAUNCH_CHECK("em_err_kernel");
+  smct::em_apply_kernel<<<1, 32, 0, st>>>(B, (const double*)scratch, logvar_k, logvar_q, logvar_v, logvar_z, it, em_param);
+  SMCT_LAUNCH_CHECK("em_apply_kernel");
+  return SMCT_OK;
+}
+
 }  // extern "C"

@@ -823,6 +823,38 @@ __global__ void __launch_bounds__(256) metric_kernel(int B, int P, int S, int Fy
 }
 
 // ------------------------------------------------------------------------------------------
+// EM variance update of src/train/utils.py:22-51 on the device.  em_err_kernel: err[w][j] = mean over (p,s,d) of
+// noise_w[j]^2 for the four recorded noises w = k,q,v,z (order of the reference's updates: v,k,q,z — the four
+// recurrences are independent) and every batch element j; em_apply_kernel: for j = 0..B-1 in order
+//   logvar <- log((1 - it^-a) exp(logvar) + it^-a err[j])        (EM_update, :48-51)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) em_err_kernel(int B, long long per_b, const float* nk, const float* nq, const float* nv,
+                                                     const float* nz, double* err) {
+  __shared__ double red[8];
+  const int w = blockIdx.x / B, j = blockIdx.x % B;
+  const float* n = (w == 0 ? nk : (w == 1 ? nq : (w == 2 ? nv : nz))) + (long long)j * per_b;
+  double acc = 0.0;
+  for (long long i = threadIdx.x; i < per_b; i += blockDim.x) { const float v = n[i]; acc += (double)v * (double)v; }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(SMCT_FULL_MASK, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0;
+    for (int i = 0; i < 8; ++i) t += red[i];
+    err[(long long)w * B + j] = t / (double)per_b;
+  }
+}
+__global__ void em_apply_kernel(int B, const double* err, float* lk, float* lq, float* lv, float* lz, float it, float em_param) {
+  const int w = threadIdx.x;
+  if (w >= 4) return;
+  float* lp = w == 0 ? lk : (w == 1 ? lq : (w == 2 ? lv : lz));
+  const float g = powf(it, -em_param);
+  float cur = lp[0];
+  for (int j = 0; j < B; ++j) cur = logf((1.0f - g) * expf(cur) + g * (float)err[(long long)w * B + j]);   // fp32 like the reference
+  lp[0] = cur;
+}
+
+// ------------------------------------------------------------------------------------------
 // small utility kernels
 // ------------------------------------------------------------------------------------------
 __global__ void fill_noise_kernel(unsigned long long seed, int which, int t, long long b0, int B, int P, int D,

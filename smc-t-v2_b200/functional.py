@@ -332,6 +332,25 @@ def classic_loss_sum(pred: torch.Tensor, y: torch.Tensor, weights="gaussian", ma
     return out
 
 
+def em_update(noises, logvars, it: float, em_param: float):
+    """EM variance update (src/train/utils.py:22-51) on the device: noises = (noise_K, noise_q, noise_V, noise_z), each
+    (B,P,S,D); logvars = the four scalar log-variance tensors (1 element each), updated IN PLACE.  No host round trip."""
+    require_cuda()
+    lib = _lib.load()
+    B = noises[0].shape[0]
+    per_b = noises[0][0].numel()
+    for n in noises:
+        if n.shape[0] != B or n[0].numel() != per_b:
+            raise ValueError("the four noises must have the same shape")
+    for lv in logvars:
+        if lv.numel() != 1:
+            raise ValueError("EM mode works on scalar log-variances (like the reference)")
+    scratch = torch.empty(4 * B, dtype=torch.float64, device=noises[0].device)
+    check(lib.smct_em_update(B, per_b, *[_ptr(n, torch.float32, "noise") for n in noises],
+                             *[_ptr(lv, torch.float32, "logvar") for lv in logvars], float(it), float(em_param),
+                             _ptr(scratch), _stream()))
+
+
 def metric_sums(pred: torch.Tensor, y: torch.Tensor, weights="gaussian", mask: Optional[torch.Tensor] = None) -> torch.Tensor:
     """(sum_{b,s} m*metric, sum_{b,s} m) of the training metric on the unresampled predictions (B,P,S,Fy): sparse CE of
     the particle-mean softmax (classification) or squared error of the particle-mean prediction (gaussian); fp64 (2,)."""

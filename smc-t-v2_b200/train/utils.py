@@ -41,22 +41,14 @@ def EM_update(err, logvar, it, EM_param):
 
 
 def EM(smc_transformer, it, EM_param):
-    """train/utils.py:22-46: per batch element j (in order) update the four scalar log-variances from the mean
-    squared noises.  Only scalar ('uni') variances, like the reference's EM mode."""
+    """train/utils.py:22-46: per batch element j (in order) update the four scalar log-variances from the mean squared
+    noises.  One smct_em_update call (two kernels, no host round trip); only scalar ('uni') variances, like the
+    reference's EM mode."""
     if not smc_transformer.cell.noise:
         return smc_transformer
     att = smc_transformer.cell.attention_smc
-    errs = {}
-    for n, noise in (("k", smc_transformer.noise_K_resampled), ("q", smc_transformer.noise_q),
-                     ("v", smc_transformer.noise_V_resampled), ("z", smc_transformer.noise_z)):
-        B = noise.shape[0]
-        per_b = torch.stack([F.sumsq_scaled(noise[j].contiguous(), torch.zeros(1, device=noise.device))[0]
-                             for j in range(B)]) / float(noise[0].numel())
-        errs[n] = per_b.cpu().tolist()
-    B = len(errs["k"])
-    for j in range(B):
-        for n in ("v", "k", "q", "z"):   # the reference's update order (:35-45)
-            var = getattr(att, "logvar_" + n)
-            cur = float(logvar_vector(var)[0].item())
-            var.assign(EM_update(errs[n][j], cur, it, EM_param))
+    noises = [smc_transformer.noise_K_resampled.contiguous(), smc_transformer.noise_q.contiguous(),
+              smc_transformer.noise_V_resampled.contiguous(), smc_transformer.noise_z.contiguous()]
+    logvars = [logvar_vector(getattr(att, "logvar_" + n)) for n in ("k", "q", "v", "z")]   # views of the variables' storage
+    F.em_update(noises, logvars, it, EM_param)
     return smc_transformer
