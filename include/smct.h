@@ -43,10 +43,11 @@ enum { SMCT_INPUT_LINEAR = 0, SMCT_INPUT_EMBEDDING = 1, SMCT_INPUT_ENCODED = 2 }
 /* FUSED: persistent kernel (two CTAs per SM, mbarrier-sequenced dense part on tcgen05, bulk-copied weights);
  * FUSED_V1: the first-generation persistent kernel (one 512-thread CTA per SM; kept for F_y > 4 and as a cross-check);
  * FUSED_FFMA: first-generation structure, dense part on CUDA cores (pure fp32 cross-check);
- * STAGED: one launch per stage and timestep, any shape; STAGED_SEQ: the staged device code in ONE launch, one CTA per
- * sequence */
+ * STAGED: one launch per stage and timestep, any shape; STAGED_SEQ: the staged device code in ONE launch, one thread-
+ * block cluster per sequence; SMALL: the reference's own small shapes (d_model 8/16/32, gaussian): one CTA per sequence,
+ * a particle's rows in the registers of d_model/8 lanes */
 enum { SMCT_ALGO_AUTO = 0, SMCT_ALGO_STAGED = 1, SMCT_ALGO_FUSED = 2, SMCT_ALGO_FUSED_FFMA = 3, SMCT_ALGO_STAGED_SEQ = 4,
-       SMCT_ALGO_FUSED_V1 = 5 };
+       SMCT_ALGO_FUSED_V1 = 5, SMCT_ALGO_SMALL = 6 };
 
 /* Problem shape + switches.  Mirrors the constructor arguments of
  * SMC_Transformer(d_model, output_size, seq_len, full_model, dff, num_heads, attn_window)

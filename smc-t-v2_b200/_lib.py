@@ -14,7 +14,7 @@ OK, ERR_INVALID, ERR_CUDA, ERR_WORKSPACE, ERR_UNSUPPORTED = 0, -1, -2, -3, -4
 WEIGHTS = {"gaussian": 0, "classification": 1}
 NOISE_Z = {"checkout": 0, "pyc": 1}
 INPUT = {"linear": 0, "embedding": 1, "encoded": 2}
-ALGO = {"auto": 0, "staged": 1, "fused": 2, "fused_ffma": 3, "staged_seq": 4, "fused_v1": 5}
+ALGO = {"auto": 0, "staged": 1, "fused": 2, "fused_ffma": 3, "staged_seq": 4, "fused_v1": 5, "small": 6}
 
 
 class SmctShape(ctypes.Structure):

@@ -12,6 +12,7 @@
 #include "../../include/smct.h"
 #include "smct_common.cuh"
 #include "smct_staged.cuh"
+#include "smct_small.cuh"
 #include "smct_fused.cuh"
 #include "smct_tc.cuh"
 #include "smct_fused_tc.cuh"
@@ -209,8 +210,29 @@ int launch_seq_t(const smct::SeqArgs& g, cudaStream_t st) {
   return SMCT_OK;
 }
 
+template <int LG, int NTHR>
+int launch_small_t(const smct::SeqArgs& g, const smct::SmallSmemLayout& L, int nthreads, cudaStream_t st) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.need()) {
+    SMCT_CUDA(cudaFuncSetAttribute(smct::small_seq_forward_kernel<LG, NTHR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+  }
+  smct::small_seq_forward_kernel<LG, NTHR><<<g.step.B, nthreads, L.total_bytes, st>>>(g, L);
+  SMCT_LAUNCH_CHECK("small_seq_forward_kernel");
+  return SMCT_OK;
+}
+
+int launch_small(const smct::SeqArgs& g, cudaStream_t st) {
+  const int D = g.step.D, LG = D / 8, P = g.step.P;
+  const smct::SmallSmemLayout L = smct::small_layout(D, g.step.dff, g.step.Fy, P);
+  if (L.total_bytes > 96 * 1024) return fail(SMCT_ERR_UNSUPPORTED, "small forward needs %d B shared memory", L.total_bytes);
+  const int nthreads = (P * LG + 31) / 32 * 32;
+  if (LG == 1) return nthreads <= 256 ? launch_small_t<1, 256>(g, L, nthreads, st) : launch_small_t<1, 1024>(g, L, nthreads, st);
+  if (LG == 2) return nthreads <= 256 ? launch_small_t<2, 256>(g, L, nthreads, st) : launch_small_t<2, 512>(g, L, nthreads, st);
+  return nthreads <= 256 ? launch_small_t<4, 256>(g, L, nthreads, st) : launch_small_t<4, 512>(g, L, nthreads, st);
+}
+
 int forward_staged(const smct_shape& s, const smct_params& pr, const smct_io& io, void* ws, size_t ws_bytes,
-                   cudaStream_t st, bool seq) {
+                   cudaStream_t st, bool seq, bool small = false) {
   if (ws_bytes < staged_forward_ws(s)) return fail(SMCT_ERR_WORKSPACE, "workspace %zu < required %zu", ws_bytes, staged_forward_ws(s));
   const int B = s.B, P = s.P, S = s.S, D = s.D;
   const size_t rows = (size_t)B * std::max(S, P);
@@ -277,7 +299,8 @@ int forward_staged(const smct_shape& s, const smct_params& pr, const smct_io& io
     g.pred = io.pred; g.noise_q = io.noise_q; g.noise_z = io.noise_z; g.attn = io.attn; g.w = io.w; g.logw_out = io.logw;
     g.i_out = io.i_out;
     int rc;
-    if (D <= 32) rc = launch_seq_t<1>(g, st);
+    if (small) rc = launch_small(g, st);
+    else if (D <= 32) rc = launch_seq_t<1>(g, st);
     else if (D <= 64) rc = launch_seq_t<2>(g, st);
     else if (D <= 128) rc = launch_seq_t<4>(g, st);
     else rc = launch_seq_t<8>(g, st);
@@ -581,6 +604,11 @@ int smct_forward(const smct_shape* shape, const smct_params* params, const smct_
   // reference's own small shapes; with more than 8 tiles per sequence (P > 256) a CTA would serialise several tiles
   // (measured on B200: C1 0.69 -> 0.44 ms, C2 0.91 -> 0.86 ms; C3 — 256 sequences x 2 tiles, more CTAs than SMs — is
   // faster on the per-stage kernels: 2.75 vs 3.75 ms, so AUTO takes the cluster form only while every CTA gets its own SM)
+  if (algo == SMCT_ALGO_SMALL || (shape->algo == SMCT_ALGO_AUTO && smct::small_supported(*shape, *io))) {
+    // the reference's own small shapes: the whole forward of a sequence in one CTA, a particle's rows in registers
+    if (!smct::small_supported(*shape, *io)) return fail(SMCT_ERR_UNSUPPORTED, "small forward does not support this shape/io");
+    return forward_staged(*shape, *params, *io, workspace, workspace_bytes, st, true, true);
+  }
   const int seq_tiles = (shape->P + smct::PT - 1) / smct::PT;
   const bool seq = (algo == SMCT_ALGO_STAGED_SEQ) ||
                    (shape->algo == SMCT_ALGO_AUTO && (seq_tiles == 1 || (seq_tiles <= 8 && (long long)shape->B * seq_tiles <= 148)));

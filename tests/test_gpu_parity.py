@@ -375,21 +375,62 @@ def test_shards_reproduce_the_full_batch(algo):
 # ----------------------------------------------------------------------------- single-launch variant of the staged path
 @pytest.mark.parametrize("name", sorted(CASES))
 def test_staged_seq_is_bit_identical_to_staged(name):
-    """SMCT_ALGO_STAGED_SEQ runs the staged device code in one launch (one CTA per sequence): identical bits, free-running,
-    with injected draws and with the device RNG; AUTO selects it for the small shapes."""
+    """SMCT_ALGO_STAGED_SEQ runs the staged device code in one launch (one thread-block cluster per sequence): identical
+    bits, free-running, with injected draws and with the device RNG."""
     c = CASES[name]
     cfg = c["cfg"]
     p, x_in, y, eps, u = util.make_case(cfg, seed=21, sigma2=c["sigma2"], multi=c.get("multi", False))
     want = ("i_out", "logw", "noise_K", "noise_V", "loss_sums", "attn")
     for kw in (dict(eps=eps, u=u), dict(eps=None, u=None, seed=5, b_global0=3)):
         ref = util.run_device(cfg, p, x_in, y, want=want, algo="staged", **kw)
-        for algo in ("staged_seq", "auto"):
-            got = util.run_device(cfg, p, x_in, y, want=want, algo=algo, **kw)
-            for k in ref:
-                if k == "loss_sums":   # fp64 atomics: the order of the adds differs between launches
-                    assert np.allclose(got[k], ref[k], rtol=1e-12, atol=0), k
-                else:
-                    assert np.array_equal(got[k], ref[k], equal_nan=True), (algo, k)
+        got = util.run_device(cfg, p, x_in, y, want=want, algo="staged_seq", **kw)
+        for k in ref:
+            if k == "loss_sums":   # fp64 atomics: the order of the adds differs between launches
+                assert np.allclose(got[k], ref[k], rtol=1e-12, atol=0), k
+            else:
+                assert np.array_equal(got[k], ref[k], equal_nan=True), k
+
+
+SMALL_CASES = ["c1", "c2_b4", "c3_b8", "window2", "stop_resampling", "multi_sigma", "p1", "s1"]
+
+
+@pytest.mark.parametrize("name", SMALL_CASES)
+def test_small_forward_matches_oracle(name):
+    """SMCT_ALGO_SMALL (the reference's own shapes: one CTA per sequence, a particle's rows in the registers of
+    d_model/8 lanes) against the oracle: teacher-forced and free-running with screened uniforms; AUTO selects it."""
+    c = CASES[name]
+    cfg = c["cfg"]
+    want = ("i_out", "logw", "noise_q", "noise_z", "noise_K", "noise_V", "loss_sums")
+    p, x_in, y, eps, u = util.make_case(cfg, seed=2, sigma2=c["sigma2"], multi=c.get("multi", False))
+    ora = O.forward(cfg, p, x_in, y, eps, u)
+    dev = util.run_device(cfg, p, x_in, y, eps, u, i_forced=ora["i_t"], want=want, algo="small")
+    util.compare_forward(cfg, p, dev, ora, y)
+    u2, ora2 = util.screen_uniforms(cfg, p, x_in, y, eps, u)
+    for algo in ("small", "auto"):
+        dev = util.run_device(cfg, p, x_in, y, eps, u2, want=want, algo=algo)
+        util.compare_forward(cfg, p, dev, ora2, y)
+
+
+def test_small_forward_device_rng_agrees_with_staged():
+    """Same seed, device RNG: the small kernel draws the same noise streams as the staged path (teacher-forced with the
+    staged path's ancestors so that a last-bit difference cannot fork the trajectories)."""
+    for name in ("c2_b4", "c3_b8"):
+        cfg = CASES[name]["cfg"]
+        p, x_in, y, _, _ = util.make_case(cfg, seed=4, sigma2=0.5)
+        want = ("i_out", "logw", "noise_q", "noise_z", "loss_sums")
+        st = util.run_device(cfg, p, x_in, y, None, None, seed=31, b_global0=7, want=want, algo="staged")
+        sm = util.run_device(cfg, p, x_in, y, None, None, seed=31, b_global0=7, i_forced=st["i_out"], want=want, algo="small")
+        for k in ("pred", "pred_resampl", "K", "V", "R", "w", "logw", "noise_q", "noise_z"):
+            util.assert_close(name + ":" + k, sm[k], st[k])
+        assert np.allclose(sm["loss_sums"][:5], st["loss_sums"][:5], rtol=2e-4)
+
+
+def test_small_forward_rejects_unsupported():
+    cfg = CASES["pyc_smoke"]["cfg"]      # d_model 6
+    p, x_in, y, eps, u = util.make_case(cfg, sigma2=0.1)
+    from smct_b200 import _lib
+    with pytest.raises(_lib.SmctError):
+        util.run_device(cfg, p, x_in, y, eps, u, algo="small")
 
 
 # ----------------------------------------------------------------------------- fp16-split operand scaling of the fused forward
