@@ -19,7 +19,7 @@ namespace smct {
 constexpr int SMALL_FY = 8;
 
 struct SmallSmemLayout {   // offsets in floats into the dynamic shared memory
-  int Wz, W1, W2, Wo, bz, b1, b2, l1g, l1b, l2g, l2b, sig, cdf_bytes_off, total_bytes;
+  int Wz, W1, W2, Wo, bz, b1, b2, l1g, l1b, l2g, l2b, sig, lw, idx, cdf_bytes_off, total_bytes;
 };
 
 inline SmallSmemLayout small_layout(int D, int dff, int Fy, int P) {
@@ -29,6 +29,7 @@ inline SmallSmemLayout small_layout(int D, int dff, int Fy, int P) {
   l.Wz = take(D * D); l.W1 = take(D * dff); l.W2 = take(dff * D); l.Wo = take(D * Fy);
   l.bz = take(D); l.b1 = take(dff); l.b2 = take(D); l.l1g = take(D); l.l1b = take(D); l.l2g = take(D); l.l2b = take(D);
   l.sig = take(6 * D);   // std k,q,v,z ; 1/var q, z
+  l.lw = take(P); l.idx = take(P);   // log-weights and drawn ancestors of the current step
   l.cdf_bytes_off = (o * 4 + 7) / 8 * 8;
   l.total_bytes = l.cdf_bytes_off + P * 8;
   return l;
@@ -105,6 +106,8 @@ __global__ void __launch_bounds__(NTHR) small_seq_forward_kernel(const SeqArgs g
   float* sbz = smf + L.bz; float* sb1 = smf + L.b1; float* sb2 = smf + L.b2;
   float* sl1g = smf + L.l1g; float* sl1b = smf + L.l1b; float* sl2g = smf + L.l2g; float* sl2b = smf + L.l2b;
   float* ssig = smf + L.sig;
+  float* slw = smf + L.lw;                                  // resample_seq indexes its arrays by b * P + p
+  int* sidx = reinterpret_cast<int*>(smf + L.idx);
   double* cdf = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(smf) + L.cdf_bytes_off);
   for (int i = tid; i < D * D; i += blockDim.x) sWz[i] = a0.p.Wz[i];
   for (int i = tid; i < D * dff; i += blockDim.x) { sW1[i] = a0.p.W1[i]; sW2[i] = a0.p.W2[i]; }
@@ -192,12 +195,12 @@ __global__ void __launch_bounds__(NTHR) small_seq_forward_kernel(const SeqArgs g
       for (int e = 0; e < 8; ++e) acc[e] = 0.f;
       const float* Kp = Kc + (bp * S) * D + d0;
       const float* Vp = Vc + (bp * S) * D + d0;
+      // (the slot-t row of this step was stored above by this very lane: reading it back from global memory keeps the
+      // loop body uniform, so that the unrolled iterations' loads are issued together instead of one L2 round trip per slot)
+#pragma unroll 4
       for (int s = s_lo; s <= t; ++s) {
         float kr[8], vr[8];
-        if (s == t) {
-#pragma unroll
-          for (int e = 0; e < 8; ++e) { kr[e] = k[e]; vr[e] = v[e]; }
-        } else {
+        {
           const float4 k0 = *reinterpret_cast<const float4*>(Kp + (long long)s * D), k1 = *reinterpret_cast<const float4*>(Kp + (long long)s * D + 4);
           const float4 v0 = *reinterpret_cast<const float4*>(Vp + (long long)s * D), v1 = *reinterpret_cast<const float4*>(Vp + (long long)s * D + 4);
           kr[0] = k0.x; kr[1] = k0.y; kr[2] = k0.z; kr[3] = k0.w; kr[4] = k1.x; kr[5] = k1.y; kr[6] = k1.z; kr[7] = k1.w;
@@ -319,7 +322,7 @@ __global__ void __launch_bounds__(NTHR) small_seq_forward_kernel(const SeqArgs g
         const float diff = ((const float*)g.y)[((long long)b * S + t) * Fy + f] - pr;
         sq = fmaf(diff, diff, sq);
       }
-      if (act && gl == 0) g.logw_ws[bp] = (-0.5f * sq) / a0.sigma_obs;
+      if (act && gl == 0) slw[pc] = (-0.5f * sq) / a0.sigma_obs;
     }
     // ---------------- loss partials of this step ----------------
     if (a0.loss_sums) {
@@ -333,14 +336,14 @@ __global__ void __launch_bounds__(NTHR) small_seq_forward_kernel(const SeqArgs g
     // ---------------- draw (TF-CPU categorical semantics) and ancestor gather ----------------
     ResampleArgs rs;
     rs.B = B; rs.P = P; rs.normalise = g.normalise;
-    rs.logw = g.logw_ws;
+    rs.logw = slw - (size_t)b * P;                         // shared memory: no global round trip between the phases
     rs.u = g.u ? g.u + (size_t)t * BP : nullptr;
     rs.i_forced = g.i_forced ? g.i_forced + (size_t)t * BP : nullptr;
     rs.seed = g.seed; rs.b_global0 = a0.b_global0; rs.t_rng = t;
     rs.w_out = g.w ? g.w + t : nullptr; rs.w_st = S;
     rs.logw_copy = g.logw_out ? g.logw_out + (size_t)t * BP : nullptr;
     rs.logits_out = nullptr;
-    rs.i_out = g.idx_ws;
+    rs.i_out = sidx - (size_t)b * P;
     rs.i_out2 = g.i_out ? g.i_out + (size_t)t * BP : nullptr;
     resample_seq(rs, b, cdf, scratch, &total_s);
     __syncthreads();
@@ -348,13 +351,26 @@ __global__ void __launch_bounds__(NTHR) small_seq_forward_kernel(const SeqArgs g
       const int rowlen4 = (t + 1) * D / 4;                 // rows 0..t as float4 (D is a multiple of 8)
       const long long stride4 = (long long)S * D / 4;
       const int n = P * rowlen4;
-      const int* idx = g.idx_ws + (size_t)b * P;
+      const int* idx = sidx;
       for (int zt = 0; zt < 3; ++zt) {
         const float4* src = reinterpret_cast<const float4*>((zt == 0 ? Kc : (zt == 1 ? Vc : Rc)) + (size_t)b * P * S * D);
         float4* dst = reinterpret_cast<float4*>((zt == 0 ? Ka : (zt == 1 ? Va : Ra)) + (size_t)b * P * S * D);
-        for (int i = tid; i < n; i += (int)blockDim.x) {
-          const int mm = i / rowlen4, off = i - mm * rowlen4;
-          dst[(long long)mm * stride4 + off] = src[(long long)idx[mm] * stride4 + off];
+        // 8 copies in flight per thread: the loads of a batch are issued before its stores (source and destination are
+        // distinct buffers, which the compiler cannot see: without this every copy pays its own L2 round trip)
+        for (int i0 = tid; i0 < n; i0 += 8 * (int)blockDim.x) {
+          float4 val[8];
+          long long da[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int i = i0 + k * (int)blockDim.x;
+            const bool ok = i < n;
+            const int mm = ok ? i / rowlen4 : 0, off = ok ? i - mm * rowlen4 : 0;
+            da[k] = ok ? (long long)mm * stride4 + off : -1;
+            val[k] = src[(long long)idx[mm] * stride4 + off];
+          }
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            if (da[k] >= 0) dst[da[k]] = val[k];
         }
       }
       float* tp;
