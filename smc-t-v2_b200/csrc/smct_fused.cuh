@@ -565,9 +565,9 @@ __global__ void __launch_bounds__(256) materialize_final_kernel(const MatArgs a)
     const float4 k4 = *reinterpret_cast<const float4*>(a.Kp + src);
     const float4 v4 = *reinterpret_cast<const float4*>(a.Vp + src);
     const float4 r4 = *reinterpret_cast<const float4*>(a.Rp + src);
-    *reinterpret_cast<float4*>(a.K + dst) = k4;
-    *reinterpret_cast<float4*>(a.V + dst) = v4;
-    *reinterpret_cast<float4*>(a.R + dst) = r4;
+    __stcs(reinterpret_cast<float4*>(a.K + dst), k4);   // streaming stores: the materialised state is not read again by the
+    __stcs(reinterpret_cast<float4*>(a.V + dst), v4);   // forward and should not evict the shared source rows from L2
+    __stcs(reinterpret_cast<float4*>(a.R + dst), r4);
     if (a.kx) {
       const long long xs = ((long long)b * a.S + s) * FD + 4 * c4;
       const float4 kx4 = *reinterpret_cast<const float4*>(a.kx + xs);
