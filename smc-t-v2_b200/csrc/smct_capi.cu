@@ -214,7 +214,7 @@ template <int LG, int NTHR>
 int launch_small_t(const smct::SeqArgs& g, const smct::SmallSmemLayout& L, int nthreads, cudaStream_t st) {
   static PerDeviceOnce attr_once;
   if (attr_once.need()) {
-    SMCT_CUDA(cudaFuncSetAttribute(smct::small_seq_forward_kernel<LG, NTHR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    SMCT_CUDA(cudaFuncSetAttribute(smct::small_seq_forward_kernel<LG, NTHR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
   }
   smct::small_seq_forward_kernel<LG, NTHR><<<g.step.B, nthreads, L.total_bytes, st>>>(g, L);
   SMCT_LAUNCH_CHECK("small_seq_forward_kernel");
@@ -223,8 +223,8 @@ int launch_small_t(const smct::SeqArgs& g, const smct::SmallSmemLayout& L, int n
 
 int launch_small(const smct::SeqArgs& g, cudaStream_t st) {
   const int D = g.step.D, LG = D / 8, P = g.step.P;
-  const smct::SmallSmemLayout L = smct::small_layout(D, g.step.dff, g.step.Fy, P);
-  if (L.total_bytes > 96 * 1024) return fail(SMCT_ERR_UNSUPPORTED, "small forward needs %d B shared memory", L.total_bytes);
+  const smct::SmallSmemLayout L = smct::small_layout(D, g.step.dff, g.step.Fy, P, g.step.S);
+  if (L.total_bytes > 208 * 1024) return fail(SMCT_ERR_UNSUPPORTED, "small forward needs %d B shared memory", L.total_bytes);
   const int nthreads = (P * LG + 31) / 32 * 32;
   if (LG == 1) return nthreads <= 256 ? launch_small_t<1, 256>(g, L, nthreads, st) : launch_small_t<1, 1024>(g, L, nthreads, st);
   if (LG == 2) return nthreads <= 256 ? launch_small_t<2, 256>(g, L, nthreads, st) : launch_small_t<2, 512>(g, L, nthreads, st);
@@ -298,9 +298,14 @@ int forward_staged(const smct_shape& s, const smct_params& pr, const smct_io& io
     }
     g.pred = io.pred; g.noise_q = io.noise_q; g.noise_z = io.noise_z; g.attn = io.attn; g.w = io.w; g.logw_out = io.logw;
     g.i_out = io.i_out;
+    if (small) {   // the small kernel's epilogue writes the final state, the output heads and the loss sums itself
+      const bool want_noise_s = io.noise_K || io.noise_V || io.loss_sums;
+      g.kx = want_noise_s ? kx : nullptr; g.vx = want_noise_s ? vx : nullptr;
+      g.pred_resampl = io.pred_resampl; g.noise_K = io.noise_K; g.noise_V = io.noise_V;
+      return launch_small(g, st);
+    }
     int rc;
-    if (small) rc = launch_small(g, st);
-    else if (D <= 32) rc = launch_seq_t<1>(g, st);
+    if (D <= 32) rc = launch_seq_t<1>(g, st);
     else if (D <= 64) rc = launch_seq_t<2>(g, st);
     else if (D <= 128) rc = launch_seq_t<4>(g, st);
     else rc = launch_seq_t<8>(g, st);

@@ -6,8 +6,12 @@
 // served by LG = d_model / 8 lanes (1, 2 or 4) that keep its q, k, v, z, o, r rows in registers (8 dims per lane) from the
 // noise generation to the log-weight, with shuffles inside the lane group for the dot products, LayerNorm statistics and
 // the small dense layers (weights in shared memory).  One barrier separates the particle phase from the draw
-// (resample_seq, shared with the staged path: TF-CPU categorical semantics) and one the draw from the ancestor gather
-// (physical copy of rows 0..t, ping-pong buffers in global memory — L2 resident at these sizes).
+// (resample_seq, shared with the staged path: TF-CPU categorical semantics) and one the draw from the genealogy update.
+// PATH STORAGE like the fused forward: K / V / R rows are written once, slot-major ([s][particle][D]; K and V in shared
+// memory when 2*S*P*D floats fit, else in the workspace), and every particle carries an ancestry row A[m][s] (uint16 in
+// shared memory, ping-pong): resampling copies t+1 indices per particle instead of 3*(t+1)*D floats.  The epilogue writes
+// K, V, R (B,P,S,D) through the final ancestry table together with the output heads of SMC_Transformer.call
+// (pred_resampl = R Wo, K - wk(X), V - wv(X)) and the loss sums — no separate final pass.
 // Served: gaussian weights, 1 head, full model, noise on, d_model in {8,16,32}, dff a multiple of LG and <= 128,
 // P * LG <= 1024, F_y <= 8, no attention-weights output.  Same RNG streams as every other path (results agree with the
 // staged path to rounding: the sums are formed in a different order).
@@ -19,17 +23,21 @@ namespace smct {
 constexpr int SMALL_FY = 8;
 
 struct SmallSmemLayout {   // offsets in floats into the dynamic shared memory
-  int Wz, W1, W2, Wo, bz, b1, b2, l1g, l1b, l2g, l2b, sig, lw, idx, cdf_bytes_off, total_bytes;
+  int Wz, W1, W2, Wo, bz, b1, b2, l1g, l1b, l2g, l2b, sig, lw, idx, anc, hist, hist_smem, cdf_bytes_off, total_bytes;
 };
 
-inline SmallSmemLayout small_layout(int D, int dff, int Fy, int P) {
+inline SmallSmemLayout small_layout(int D, int dff, int Fy, int P, int S) {
   SmallSmemLayout l;
   int o = 0;
   auto take = [&](int n) { int r = o; o += (n + 3) / 4 * 4; return r; };
   l.Wz = take(D * D); l.W1 = take(D * dff); l.W2 = take(dff * D); l.Wo = take(D * Fy);
   l.bz = take(D); l.b1 = take(dff); l.b2 = take(D); l.l1g = take(D); l.l1b = take(D); l.l2g = take(D); l.l2b = take(D);
-  l.sig = take(6 * D);   // std k,q,v,z ; 1/var q, z
+  l.sig = take(8 * D);   // std k,q,v,z ; 1/var q, z, k, v
   l.lw = take(P); l.idx = take(P);   // log-weights and drawn ancestors of the current step
+  l.anc = take(P * S);               // two ancestry tables of P*S uint16 (= P*S floats)
+  const long long hist_floats = 2LL * S * P * D;
+  l.hist_smem = ((long long)(o + hist_floats) * 4 + (long long)P * 8 + 64 <= 200LL * 1024) ? 1 : 0;   // K, V rows in shared memory
+  l.hist = l.hist_smem ? take((int)hist_floats) : 0;
   l.cdf_bytes_off = (o * 4 + 7) / 8 * 8;
   l.total_bytes = l.cdf_bytes_off + P * 8;
   return l;
@@ -120,12 +128,17 @@ __global__ void __launch_bounds__(NTHR) small_seq_forward_kernel(const SeqArgs g
     ssig[i] = expf(0.5f * a0.p.logvar_k[li]); ssig[D + i] = expf(0.5f * a0.p.logvar_q[li]);
     ssig[2 * D + i] = expf(0.5f * a0.p.logvar_v[li]); ssig[3 * D + i] = expf(0.5f * a0.p.logvar_z[li]);
     ssig[4 * D + i] = expf(-a0.p.logvar_q[li]); ssig[5 * D + i] = expf(-a0.p.logvar_z[li]);
+    ssig[6 * D + i] = expf(-a0.p.logvar_k[li]); ssig[7 * D + i] = expf(-a0.p.logvar_v[li]);
   }
   __syncthreads();
 
-  float *Kc, *Vc, *Rc, *Ka, *Va, *Ra;
-  if (g.n_gather % 2 == 0) { Kc = g.K0; Vc = g.V0; Rc = g.R0; Ka = g.K2; Va = g.V2; Ra = g.R2; }
-  else { Kc = g.K2; Vc = g.V2; Rc = g.R2; Ka = g.K0; Va = g.V0; Ra = g.R0; }
+  // physical rows, slot-major [s][particle][D]: K, V in shared memory when they fit, else in the workspace; R in the workspace
+  const size_t seq_off = (size_t)b * S * P * D;
+  float* const Kph = L.hist_smem ? (smf + L.hist) : (g.K2 + seq_off);
+  float* const Vph = L.hist_smem ? (smf + L.hist + (size_t)S * P * D) : (g.V2 + seq_off);
+  float* const Rph = g.R2 + seq_off;
+  unsigned short* Acur = reinterpret_cast<unsigned short*>(smf + L.anc);     // A[m][s]: physical row of particle m at slot s
+  unsigned short* Anxt = Acur + (size_t)P * S;
   const long long bp = (long long)b * P + pc;
   const unsigned long long gbp = (unsigned long long)(a0.b_global0 + b) * (unsigned long long)P + pc;
   const float inv_sqrt_d = 1.0f / sqrtf((float)D);
@@ -174,8 +187,8 @@ __global__ void __launch_bounds__(NTHR) small_seq_forward_kernel(const SeqArgs g
         loss_q = act ? fmaf(nq[e] * nq[e], ssig[4 * D + d0 + e], loss_q) : loss_q;
       }
       if (act) {
-        float* kd = Kc + (bp * S + t) * D + d0;
-        float* vd = Vc + (bp * S + t) * D + d0;
+        float* kd = Kph + ((size_t)t * P + pc) * D + d0;
+        float* vd = Vph + ((size_t)t * P + pc) * D + d0;
         *reinterpret_cast<float4*>(kd) = make_float4(k[0], k[1], k[2], k[3]);
         *reinterpret_cast<float4*>(kd + 4) = make_float4(k[4], k[5], k[6], k[7]);
         *reinterpret_cast<float4*>(vd) = make_float4(v[0], v[1], v[2], v[3]);
@@ -193,16 +206,16 @@ __global__ void __launch_bounds__(NTHR) small_seq_forward_kernel(const SeqArgs g
       float m = -INFINITY, l = 0.f, acc[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-      const float* Kp = Kc + (bp * S) * D + d0;
-      const float* Vp = Vc + (bp * S) * D + d0;
-      // (the slot-t row of this step was stored above by this very lane: reading it back from global memory keeps the
-      // loop body uniform, so that the unrolled iterations' loads are issued together instead of one L2 round trip per slot)
+      const unsigned short* Arow = Acur + (size_t)pc * S;
+      // (the slot-t row of this step was stored above by this very lane: reading it back keeps the loop body uniform, so
+      // that the unrolled iterations' loads are issued together)
 #pragma unroll 4
       for (int s = s_lo; s <= t; ++s) {
         float kr[8], vr[8];
         {
-          const float4 k0 = *reinterpret_cast<const float4*>(Kp + (long long)s * D), k1 = *reinterpret_cast<const float4*>(Kp + (long long)s * D + 4);
-          const float4 v0 = *reinterpret_cast<const float4*>(Vp + (long long)s * D), v1 = *reinterpret_cast<const float4*>(Vp + (long long)s * D + 4);
+          const size_t ro = ((size_t)s * P + (s == t ? pc : (int)Arow[s])) * D + d0;
+          const float4 k0 = *reinterpret_cast<const float4*>(Kph + ro), k1 = *reinterpret_cast<const float4*>(Kph + ro + 4);
+          const float4 v0 = *reinterpret_cast<const float4*>(Vph + ro), v1 = *reinterpret_cast<const float4*>(Vph + ro + 4);
           kr[0] = k0.x; kr[1] = k0.y; kr[2] = k0.z; kr[3] = k0.w; kr[4] = k1.x; kr[5] = k1.y; kr[6] = k1.z; kr[7] = k1.w;
           vr[0] = v0.x; vr[1] = v0.y; vr[2] = v0.z; vr[3] = v0.w; vr[4] = v1.x; vr[5] = v1.y; vr[6] = v1.z; vr[7] = v1.w;
         }
@@ -305,7 +318,7 @@ __global__ void __launch_bounds__(NTHR) small_seq_forward_kernel(const SeqArgs g
         r[e] = r[e] * inv + (sl2b[d0 + e] - mean * inv);
       }
       if (act) {
-        float* rd = Rc + (bp * S + t) * D + d0;
+        float* rd = Rph + ((size_t)t * P + pc) * D + d0;
         *reinterpret_cast<float4*>(rd) = make_float4(r[0], r[1], r[2], r[3]);
         *reinterpret_cast<float4*>(rd + 4) = make_float4(r[4], r[5], r[6], r[7]);
       }
@@ -347,35 +360,82 @@ __global__ void __launch_bounds__(NTHR) small_seq_forward_kernel(const SeqArgs g
     rs.i_out2 = g.i_out ? g.i_out + (size_t)t * BP : nullptr;
     resample_seq(rs, b, cdf, scratch, &total_s);
     __syncthreads();
+    // ---------------- genealogy update: A_new[m][0..t) = A[idx[m]][0..t), A_new[m][t] = idx[m] ----------------
     if (g.len_resampling < 0 || t < g.len_resampling) {
-      const int rowlen4 = (t + 1) * D / 4;                 // rows 0..t as float4 (D is a multiple of 8)
-      const long long stride4 = (long long)S * D / 4;
-      const int n = P * rowlen4;
-      const int* idx = sidx;
-      for (int zt = 0; zt < 3; ++zt) {
-        const float4* src = reinterpret_cast<const float4*>((zt == 0 ? Kc : (zt == 1 ? Vc : Rc)) + (size_t)b * P * S * D);
-        float4* dst = reinterpret_cast<float4*>((zt == 0 ? Ka : (zt == 1 ? Va : Ra)) + (size_t)b * P * S * D);
-        // 8 copies in flight per thread: the loads of a batch are issued before its stores (source and destination are
-        // distinct buffers, which the compiler cannot see: without this every copy pays its own L2 round trip)
-        for (int i0 = tid; i0 < n; i0 += 8 * (int)blockDim.x) {
-          float4 val[8];
-          long long da[8];
+      const int n = P * (t + 1);
+      for (int i = tid; i < n; i += (int)blockDim.x) {
+        const int mm = i / (t + 1), sl = i - mm * (t + 1);
+        const int src = sidx[mm];
+        Anxt[(size_t)mm * S + sl] = (sl == t) ? (unsigned short)src : Acur[(size_t)src * S + sl];
+      }
+      unsigned short* tp = Acur; Acur = Anxt; Anxt = tp;
+    } else {
+      for (int mm = tid; mm < P; mm += (int)blockDim.x) Acur[(size_t)mm * S + t] = (unsigned short)mm;
+    }
+    __syncthreads();
+  }
+
+  // ---------------- epilogue: K, V, R (B,P,S,D) through the final ancestry table + the output heads + loss sums ----------------
+  {
+    float lk = 0.f, lv = 0.f, ly = 0.f;
+    const unsigned short* Arow = Acur + (size_t)pc * S;
+#pragma unroll 2
+    for (int s2 = 0; s2 < S; ++s2) {
+      const size_t ro = ((size_t)s2 * P + Arow[s2]) * D + d0;
+      const float4 k0 = *reinterpret_cast<const float4*>(Kph + ro), k1 = *reinterpret_cast<const float4*>(Kph + ro + 4);
+      const float4 v0 = *reinterpret_cast<const float4*>(Vph + ro), v1 = *reinterpret_cast<const float4*>(Vph + ro + 4);
+      const float4 r0 = *reinterpret_cast<const float4*>(Rph + ro), r1 = *reinterpret_cast<const float4*>(Rph + ro + 4);
+      const size_t dst = ((size_t)bp * S + s2) * D + d0;
+      if (act) {
+        *reinterpret_cast<float4*>(g.K0 + dst) = k0; *reinterpret_cast<float4*>(g.K0 + dst + 4) = k1;
+        *reinterpret_cast<float4*>(g.V0 + dst) = v0; *reinterpret_cast<float4*>(g.V0 + dst + 4) = v1;
+        *reinterpret_cast<float4*>(g.R0 + dst) = r0; *reinterpret_cast<float4*>(g.R0 + dst + 4) = r1;
+      }
+      if (g.kx) {   // noise_K = K - wk(X), noise_V = V - wv(X) with the un-normalised X (SMC_Transformer.py:235-236)
+        const size_t xs = ((size_t)b * S + s2) * D + d0;
+        const float4 a0k = *reinterpret_cast<const float4*>(g.kx + xs), a1k = *reinterpret_cast<const float4*>(g.kx + xs + 4);
+        const float4 a0v = *reinterpret_cast<const float4*>(g.vx + xs), a1v = *reinterpret_cast<const float4*>(g.vx + xs + 4);
+        const float nk[8] = {k0.x - a0k.x, k0.y - a0k.y, k0.z - a0k.z, k0.w - a0k.w, k1.x - a1k.x, k1.y - a1k.y, k1.z - a1k.z, k1.w - a1k.w};
+        const float nv[8] = {v0.x - a0v.x, v0.y - a0v.y, v0.z - a0v.z, v0.w - a0v.w, v1.x - a1v.x, v1.y - a1v.y, v1.z - a1v.z, v1.w - a1v.w};
+        if (act && g.noise_K) {
+          *reinterpret_cast<float4*>(g.noise_K + dst) = make_float4(nk[0], nk[1], nk[2], nk[3]);
+          *reinterpret_cast<float4*>(g.noise_K + dst + 4) = make_float4(nk[4], nk[5], nk[6], nk[7]);
+        }
+        if (act && g.noise_V) {
+          *reinterpret_cast<float4*>(g.noise_V + dst) = make_float4(nv[0], nv[1], nv[2], nv[3]);
+          *reinterpret_cast<float4*>(g.noise_V + dst + 4) = make_float4(nv[4], nv[5], nv[6], nv[7]);
+        }
+        if (act) {
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const int i = i0 + k * (int)blockDim.x;
-            const bool ok = i < n;
-            const int mm = ok ? i / rowlen4 : 0, off = ok ? i - mm * rowlen4 : 0;
-            da[k] = ok ? (long long)mm * stride4 + off : -1;
-            val[k] = src[(long long)idx[mm] * stride4 + off];
+          for (int e = 0; e < 8; ++e) {
+            lk = fmaf(nk[e] * nk[e], ssig[6 * D + d0 + e], lk);
+            lv = fmaf(nv[e] * nv[e], ssig[7 * D + d0 + e], lv);
           }
-#pragma unroll
-          for (int k = 0; k < 8; ++k)
-            if (da[k] >= 0) dst[da[k]] = val[k];
         }
       }
-      float* tp;
-      tp = Kc; Kc = Ka; Ka = tp; tp = Vc; Vc = Va; Va = tp; tp = Rc; Rc = Ra; Ra = tp;
+      const float rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+      for (int f = 0; f < Fy; ++f) {
+        float part = 0.f;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) part = fmaf(rr[e], sWo[(d0 + e) * Fy + f], part);
+        const float pr = group_allsum<LG>(part);
+        if (act && gl == 0) {
+          if (g.pred_resampl) g.pred_resampl[((size_t)bp * S + s2) * Fy + f] = pr;
+          const float diff = ((const float*)g.y)[((size_t)b * S + s2) * Fy + f] - pr;
+          ly = fmaf(diff, diff, ly);
+        }
+      }
+    }
+    if (a0.loss_sums) {
+      lk = warp_sum(lk); lv = warp_sum(lv); ly = warp_sum(ly);
       __syncthreads();
+      if (lane == 0) { redl[wid] = lk; redl[32 + wid] = lv; scratch[wid] = ly; }
+      __syncthreads();
+      if (tid == 0) {
+        double s0 = 0, s1 = 0, s2 = 0;
+        for (int i = 0; i < nw; ++i) { s0 += (double)redl[i]; s1 += (double)redl[32 + i]; s2 += (double)scratch[i]; }
+        atomicAdd(a0.loss_sums + 0, s0); atomicAdd(a0.loss_sums + 2, s1); atomicAdd(a0.loss_sums + 4, s2);
+      }
     }
   }
   if (tid == 0 && a0.loss_sums) { atomicAdd(a0.loss_sums + 1, dloss_q); atomicAdd(a0.loss_sums + 3, dloss_z); }

@@ -621,6 +621,9 @@ struct SeqArgs {
   float* logw_ws; int* idx_ws;   // (B,P) scratch
   float *pred, *noise_q, *noise_z, *attn, *w, *logw_out;
   int* i_out;
+  // SMCT_ALGO_SMALL only (its epilogue replaces final_kernel): (B,S,D) rows wk(X), wv(X); output heads
+  const float *kx, *vx;
+  float *pred_resampl, *noise_K, *noise_V;
 };
 
 // A sequence is served by a thread-block CLUSTER of CL CTAs (CL = 1: the plain one-CTA-per-sequence form): CTA `rank`
