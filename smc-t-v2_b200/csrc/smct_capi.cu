@@ -480,7 +480,7 @@ int forward_fused(const smct_shape& s, const smct_params& pr, const smct_io& io,
   m.y = io.loss_sums ? (const float*)io.y : nullptr;
   m.K = io.K; m.V = io.V; m.R = io.R;
   m.pred_resampl = io.pred_resampl; m.noise_K = io.noise_K; m.noise_V = io.noise_V; m.loss_sums = io.loss_sums;
-  smct::materialize_final_kernel<<<(unsigned)((long long)B * P), 256, 0, st>>>(m);
+  smct::materialize_final_kernel<<<(unsigned)((long long)B * ((P + smct::MAT_PB - 1) / smct::MAT_PB)), 256, 0, st>>>(m);
   SMCT_LAUNCH_CHECK("materialize_final_kernel");
   return SMCT_OK;
 }

@@ -79,11 +79,18 @@ __device__ __forceinline__ float u01_f32(uint32_t x) {
   return (float)(x >> 9) * 1.1920928955078125e-07f + 5.9604644775390625e-08f;  // 2^-23, 2^-24
 }
 
+// Box-Muller on two 23-bit uniforms in (0,1).  The special-function unit is used directly (lg2 / sqrt / sin / cos
+// .approx): u1 >= 2^-24 is never denormal and -2 ln u1 is in (0, 33.3], so the denormal scaling of __logf and the
+// range check + Newton step + slow-path call of the IEEE sqrtf are dead weight here — 15 instead of 30 SASS
+// instructions per pair and no divergence barrier, at 256 normals per particle-step.
 __device__ __forceinline__ void box_muller(uint32_t xa, uint32_t xb, float& n0, float& n1) {
-  const float u1 = u01_f32(xa), u2 = u01_f32(xb);
-  const float r = sqrtf(-2.0f * __logf(u1));
-  float s, c;
-  __sincosf(6.283185307179586f * (u2 - 0.5f), &s, &c);
+  const float u1 = u01_f32(xa);
+  const float th = fmaf((float)(xb >> 9), 7.4901405658e-07f, -3.1415922791f);   // 2 pi (u2 - 1/2), u2 = x 2^-23 + 2^-24
+  float l2, r, s, c;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(u1));
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(l2 * -1.3862943611198906f));   // sqrt(-2 ln u1)
+  asm("sin.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(th));
+  asm("cos.approx.ftz.f32 %0, %1;" : "=f"(c) : "f"(th));
   n0 = r * c; n1 = r * s;
 }
 

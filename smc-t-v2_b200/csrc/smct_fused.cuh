@@ -527,7 +527,14 @@ __global__ void __launch_bounds__(FNT, 1) fused_forward_kernel(const FusedArgs a
 // materialize_final_kernel: K,V,R (B,P,S,64) <- slot-major physical rows through the final ancestry table,
 // fused with the output heads of SMC_Transformer.call (SMC_Transformer.py:231-236): pred_resampl = R·Wo,
 // noise_K = K - wk(X), noise_V = V - wv(X) and the loss sums — one pass over the state instead of two.
-// One CTA per (b, logical particle); a half-warp (16 lanes x float4) owns one 64-float row.
+//
+// A pure 3 x (B,P,S,64) fp32 write stream (29.8 GB per 296 C4 sequences; a plain fill of that size takes 4.0 ms on this
+// part), so the kernel is built for memory-level parallelism: one CTA walks MAT_PB logical particles of one sequence; a
+// half-warp (16 lanes x float4) owns 8 consecutive rows of a particle, reads their 8 ancestry entries as ONE 16-byte
+// word (requested one particle ahead), and keeps 12 independent row loads in flight per thread before the first
+// store.  The output-layer dot products of 4 rows are reduced with a 5-shuffle transpose instead of 16 shuffles.
+// (The first version handled one row per loop trip behind a pos -> ancestry -> row dependency chain: 7.7 ms, long
+// scoreboard 9 warps per issue slot, profiles/r02_materialize_summary.md.)
 // ------------------------------------------------------------------------------------------
 struct MatArgs {
   int B, P, S, Sa, Fy, logvar_dim;
@@ -541,15 +548,25 @@ struct MatArgs {
   double* loss_sums;         // [0] K, [2] V, [4] sum (y - pred_resampl)^2
 };
 
-__global__ void __launch_bounds__(256) materialize_final_kernel(const MatArgs a) {
+constexpr int MAT_PB = 4;    // logical particles per CTA
+
+__device__ __forceinline__ float4 sub4(const float4 x, const float4 y) {
+  return make_float4(x.x - y.x, x.y - y.y, x.z - y.z, x.w - y.w);
+}
+
+__global__ void __launch_bounds__(256, 2) materialize_final_kernel(const MatArgs a) {
   __shared__ double red[3][8];
-  const long long bp = blockIdx.x;
-  const int b = (int)(bp / a.P);
-  const int q = a.pos[bp];
-  const unsigned short* Arow = (a.aflag[b] ? a.A0 : a.A1) + ((long long)b * a.P + q) * a.Sa;
-  const int tid = threadIdx.x, c4 = tid & 15, lane = tid & 31, wid = tid >> 5;
+  const int pblocks = (a.P + MAT_PB - 1) / MAT_PB;
+  const int b = (int)(blockIdx.x / pblocks);
+  const int p0 = (int)(blockIdx.x % pblocks) * MAT_PB;
+  const int pn = min(MAT_PB, a.P - p0);
+  const int tid = threadIdx.x, c4 = tid & 15, g = tid >> 4, lane = tid & 31, wid = tid >> 5;
   const unsigned hmask = (lane & 16) ? 0xFFFF0000u : 0x0000FFFFu;   // shuffles stay inside the half-warp
-  const int Fy = a.Fy;
+  const int Fy = a.Fy, S = a.S, P = a.P;
+  const unsigned short* const Ab = (a.aflag[b] ? a.A0 : a.A1) + (long long)b * P * a.Sa;
+  const unsigned short* const posb = a.pos + (long long)b * P;
+  const int npass = (S + 127) >> 7;            // 128 rows per pass: half-warp g owns rows 128 pass + 8 g .. + 7
+  const int nit = pn * npass;
   float ivk[4], ivv[4];
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
@@ -557,41 +574,87 @@ __global__ void __launch_bounds__(256) materialize_final_kernel(const MatArgs a)
     ivk[e] = a.kx ? expf(-a.logvar_k[d]) : 0.f;
     ivv[e] = a.kx ? expf(-a.logvar_v[d]) : 0.f;
   }
+  // ancestry entries of (iteration it) = (particle it / npass, pass it % npass); Sa is a multiple of 8 and s0 < S <= Sa
+  auto load_anc = [&](int it) -> uint4 {
+    const int pi = it / npass, s0 = ((it - pi * npass) << 7) + 8 * g;
+    if (it >= nit || s0 >= S) return make_uint4(0u, 0u, 0u, 0u);
+    const int q = posb[p0 + pi];
+    return *reinterpret_cast<const uint4*>(Ab + (long long)q * a.Sa + s0);
+  };
   float lk = 0.f, lv = 0.f, ly = 0.f;
-  for (int s = tid >> 4; s < a.S; s += 16) {
-    const int row = Arow[s];
-    const long long src = (((long long)b * a.S + s) * a.P + row) * FD + 4 * c4;
-    const long long dst = (bp * a.S + s) * FD + 4 * c4;
-    const float4 k4 = *reinterpret_cast<const float4*>(a.Kp + src);
-    const float4 v4 = *reinterpret_cast<const float4*>(a.Vp + src);
-    const float4 r4 = *reinterpret_cast<const float4*>(a.Rp + src);
-    __stcs(reinterpret_cast<float4*>(a.K + dst), k4);   // streaming stores: the materialised state is not read again by the
-    __stcs(reinterpret_cast<float4*>(a.V + dst), v4);   // forward and should not evict the shared source rows from L2
-    __stcs(reinterpret_cast<float4*>(a.R + dst), r4);
-    if (a.kx) {
-      const long long xs = ((long long)b * a.S + s) * FD + 4 * c4;
-      const float4 kx4 = *reinterpret_cast<const float4*>(a.kx + xs);
-      const float4 vx4 = *reinterpret_cast<const float4*>(a.vx + xs);
-      const float4 nk = make_float4(k4.x - kx4.x, k4.y - kx4.y, k4.z - kx4.z, k4.w - kx4.w);
-      const float4 nv = make_float4(v4.x - vx4.x, v4.y - vx4.y, v4.z - vx4.z, v4.w - vx4.w);
-      if (a.noise_K) *reinterpret_cast<float4*>(a.noise_K + dst) = nk;
-      if (a.noise_V) *reinterpret_cast<float4*>(a.noise_V + dst) = nv;
-      lk = fmaf(nk.x * nk.x, ivk[0], fmaf(nk.y * nk.y, ivk[1], fmaf(nk.z * nk.z, ivk[2], fmaf(nk.w * nk.w, ivk[3], lk))));
-      lv = fmaf(nv.x * nv.x, ivv[0], fmaf(nv.y * nv.y, ivv[1], fmaf(nv.z * nv.z, ivv[2], fmaf(nv.w * nv.w, ivv[3], lv))));
-    }
-    if (a.pred_resampl || a.y) {
-      for (int f = 0; f < Fy; ++f) {
-        const float* w = a.Wo + (4 * c4) * Fy + f;
-        float part = fmaf(r4.x, __ldg(w), fmaf(r4.y, __ldg(w + Fy), fmaf(r4.z, __ldg(w + 2 * Fy), r4.w * __ldg(w + 3 * Fy))));
-        part += __shfl_xor_sync(hmask, part, 1);
-        part += __shfl_xor_sync(hmask, part, 2);
-        part += __shfl_xor_sync(hmask, part, 4);
-        part += __shfl_xor_sync(hmask, part, 8);
-        if (c4 == 0) {
-          if (a.pred_resampl) a.pred_resampl[(bp * a.S + s) * Fy + f] = part;
-          if (a.y) {
-            const float diff = a.y[((long long)b * a.S + s) * Fy + f] - part;
-            ly = fmaf(diff, diff, ly);
+  uint4 av_next = load_anc(0);
+  for (int it = 0; it < nit; ++it) {
+    const uint4 av = av_next;
+    av_next = load_anc(it + 1);
+    const int pi = it / npass, s0 = ((it - pi * npass) << 7) + 8 * g;
+    const long long bp = (long long)b * P + p0 + pi;
+    const uint32_t aw[4] = {av.x, av.y, av.z, av.w};
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int sb = s0 + 4 * half;
+      float4 k4[4], v4[4], r4[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int s = sb + j;
+        const uint32_t w = aw[2 * half + (j >> 1)];
+        const int row = (j & 1) ? (int)(w >> 16) : (int)(w & 0xFFFFu);
+        k4[j] = v4[j] = r4[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (s < S) {
+          const long long src = (((long long)b * S + s) * P + row) * FD + 4 * c4;
+          k4[j] = *reinterpret_cast<const float4*>(a.Kp + src);
+          v4[j] = *reinterpret_cast<const float4*>(a.Vp + src);
+          r4[j] = *reinterpret_cast<const float4*>(a.Rp + src);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int s = sb + j;
+        if (s < S) {
+          const long long dst = (bp * S + s) * FD + 4 * c4;
+          __stcs(reinterpret_cast<float4*>(a.K + dst), k4[j]);   // streaming stores: the materialised state is not read again
+          __stcs(reinterpret_cast<float4*>(a.V + dst), v4[j]);   // by the forward and should not evict the shared source rows
+          __stcs(reinterpret_cast<float4*>(a.R + dst), r4[j]);
+        }
+      }
+      if (a.kx) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int s = sb + j;
+          if (s < S) {
+            const long long xs = ((long long)b * S + s) * FD + 4 * c4;
+            const long long dst = (bp * S + s) * FD + 4 * c4;
+            const float4 nk = sub4(k4[j], *reinterpret_cast<const float4*>(a.kx + xs));
+            const float4 nv = sub4(v4[j], *reinterpret_cast<const float4*>(a.vx + xs));
+            if (a.noise_K) *reinterpret_cast<float4*>(a.noise_K + dst) = nk;
+            if (a.noise_V) *reinterpret_cast<float4*>(a.noise_V + dst) = nv;
+            lk = fmaf(nk.x * nk.x, ivk[0], fmaf(nk.y * nk.y, ivk[1], fmaf(nk.z * nk.z, ivk[2], fmaf(nk.w * nk.w, ivk[3], lk))));
+            lv = fmaf(nv.x * nv.x, ivv[0], fmaf(nv.y * nv.y, ivv[1], fmaf(nv.z * nv.z, ivv[2], fmaf(nv.w * nv.w, ivv[3], lv))));
+          }
+        }
+      }
+      if (a.pred_resampl || a.y) {
+        // the half-warp's 4 rows x Fy outputs: per-lane partial dot products, then a transpose-reduce over the 16 lanes
+        // (xor 8: 4 -> 2 values, xor 4: 2 -> 1, xor 2, xor 1); lane l ends with row 2 bit3(l) + bit2(l)
+        const bool up8 = (c4 & 8) != 0, up4 = (c4 & 4) != 0;
+        const int jr = (up8 ? 2 : 0) + (up4 ? 1 : 0);
+        const int s = sb + jr;
+        for (int f = 0; f < Fy; ++f) {
+          const float* w = a.Wo + (4 * c4) * Fy + f;
+          const float w0 = __ldg(w), w1 = __ldg(w + Fy), w2 = __ldg(w + 2 * Fy), w3 = __ldg(w + 3 * Fy);
+          float pt[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) pt[j] = fmaf(r4[j].x, w0, fmaf(r4[j].y, w1, fmaf(r4[j].z, w2, r4[j].w * w3)));
+          const float q0 = (up8 ? pt[2] : pt[0]) + __shfl_xor_sync(hmask, up8 ? pt[0] : pt[2], 8);
+          const float q1 = (up8 ? pt[3] : pt[1]) + __shfl_xor_sync(hmask, up8 ? pt[1] : pt[3], 8);
+          float part = (up4 ? q1 : q0) + __shfl_xor_sync(hmask, up4 ? q0 : q1, 4);
+          part += __shfl_xor_sync(hmask, part, 2);
+          part += __shfl_xor_sync(hmask, part, 1);
+          if ((c4 & 3) == 0 && s < S) {
+            if (a.pred_resampl) a.pred_resampl[(bp * S + s) * Fy + f] = part;
+            if (a.y) {
+              const float diff = a.y[((long long)b * S + s) * Fy + f] - part;
+              ly = fmaf(diff, diff, ly);
+            }
           }
         }
       }
