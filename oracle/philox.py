@@ -10,12 +10,12 @@ the categorical draw are exact: integer -> fp64), and (b) check the device norma
 (device logf/sincosf differ from numpy's in the last ulps; parity tests therefore read the normals
 back from the device fill entry point ``smct_fill_noise`` and inject those into the oracle).
 
-Stream layout (must match smc-t-v2_b200/csrc/smct_rng.cuh):
+Stream layout (must match smc-t-v2_b200/csrc/smct_common.cuh):
   key     = (seed_lo, seed_hi)
   counter = (group_lo, group_hi, stream, t)
   stream  : 0=eps_k 1=eps_q 2=eps_v 3=eps_z 4=uniform
   normals : group = (b_global*P + p) * ceil(D/4) + d//4, element d%4 of the 4 outputs
-            (x0,x1)->Box-Muller->(n0,n1), (x2,x3)->(n2,n3)
+            (x0,x1)->Box-Muller->(n0,n1), (x2,x3)->(n2,n3); u1 = fl32(x0) 2^-32 + 2^-33, angle from fl32(x1)
   uniform : group = b_global*P + p ; u = ((x0>>5)*2^26 + (x1>>6)) * 2^-53
 """
 import numpy as np
@@ -52,16 +52,15 @@ def philox4x32(c0, c1, c2, c3, k0, k1, rounds=ROUNDS):
     return tuple(c.astype(np.uint32) for c in (c0, c1, c2, c3))
 
 
-def _u01_f32(x):
-    """(x>>9) * 2^-23 + 2^-24  in (0,1), exactly representable in fp32."""
-    return ((x >> np.uint32(9)).astype(np.float32) * np.float32(2.0 ** -23) + np.float32(2.0 ** -24)).astype(np.float32)
-
-
 def box_muller(xa, xb):
-    u1 = _u01_f32(xa)
-    u2 = _u01_f32(xb)
+    """u1 = fl32(xa) 2^-32 + 2^-33 in (0,1] (one fused multiply-add, like the device), angle = fl32(xb) 2pi 2^-32 - pi(1-2^-32);
+    r = sqrt(-2 ln u1).  The device evaluates lg2 / sqrt / sin / cos on the special-function unit, so the normals agree to
+    float tolerance, not bit for bit."""
+    fa = np.asarray(xa, np.uint32).astype(np.float32).astype(np.float64)
+    fb = np.asarray(xb, np.uint32).astype(np.float32).astype(np.float64)
+    u1 = (fa * float(np.float32(2.0 ** -32)) + float(np.float32(2.0 ** -33))).astype(np.float32)
+    th = (fb * float(np.float32(1.4629180792671596e-09)) + float(np.float32(-3.1415926528583237))).astype(np.float32)
     r = np.sqrt(np.float32(-2.0) * np.log(u1, dtype=np.float32), dtype=np.float32)
-    th = (np.float32(6.283185307179586) * (u2 - np.float32(0.5))).astype(np.float32)
     return (r * np.cos(th, dtype=np.float32)).astype(np.float32), (r * np.sin(th, dtype=np.float32)).astype(np.float32)
 
 

@@ -1,6 +1,7 @@
 // smct_common.cuh — shared device helpers: warp/block reductions, Philox4x32-7 + Box-Muller,
 // LayerNorm (Keras non-fused form).  sm_100a only.
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <math.h>
@@ -53,6 +54,23 @@ __device__ __forceinline__ float block_max(float v, float* scratch) {
 }
 
 // ------------------------------------------------------------------------------------------
+// fp16 (h, m) split of a pair of fp32 values (the operand format of every tensor-core product of the fused forward:
+// x = h + m to ~22 bits, smct_tc.cuh).  One packed conversion per pair (F2FP.SATFINITE.F16.F32.PACK_AB): the saturating
+// form keeps out-of-range values finite (+-65504) without separate clamps, and is the same round-to-nearest conversion
+// in range.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t pack_half2_sat(float lo, float hi) {
+  uint32_t h;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(hi), "f"(lo));
+  return h;
+}
+__device__ __forceinline__ void split_half2(float x, float y, uint32_t& h, uint32_t& m) {
+  h = pack_half2_sat(x, y);
+  const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&h));
+  m = pack_half2_sat(x - hf.x, y - hf.y);
+}
+
+// ------------------------------------------------------------------------------------------
 // Philox4x32-R (Salmon et al. SC'11).  Stream layout documented in oracle/philox.py:
 //   key = (seed_lo, seed_hi); counter = (group_lo, group_hi, stream, t)
 // R = 7 rounds: the smallest round count the Random123 authors report as passing BigCrush ("Philox4x32-7"); the noise
@@ -75,17 +93,15 @@ __device__ __forceinline__ u32x4 philox4x32(uint32_t c0, uint32_t c1, uint32_t c
   return u32x4{c0, c1, c2, c3};
 }
 
-__device__ __forceinline__ float u01_f32(uint32_t x) {
-  return (float)(x >> 9) * 1.1920928955078125e-07f + 5.9604644775390625e-08f;  // 2^-23, 2^-24
-}
-
-// Box-Muller on two 23-bit uniforms in (0,1).  The special-function unit is used directly (lg2 / sqrt / sin / cos
-// .approx): u1 >= 2^-24 is never denormal and -2 ln u1 is in (0, 33.3], so the denormal scaling of __logf and the
-// range check + Newton step + slow-path call of the IEEE sqrtf are dead weight here — 15 instead of 30 SASS
-// instructions per pair and no divergence barrier, at 256 normals per particle-step.
+// Box-Muller on two 32-bit words.  u1 = fl(x) 2^-32 + 2^-33 in (0, 1] (the int -> float conversion rounds to 24 bits, so
+// no shift is needed; u1 = 1 gives r = 0), angle = 2 pi (u2 - 1/2) as one FMA of the converted word.  The
+// special-function unit is used directly (lg2 / sqrt / sin / cos .approx): u1 >= 2^-33 is never denormal and
+// -2 ln u1 is in [0, 45.8], so the denormal scaling of __logf and the range check + Newton step + slow-path call of
+// the IEEE sqrtf are dead weight here — 13 instead of 30 SASS instructions per pair and no divergence barrier, at
+// 256 normals per particle-step.  oracle/philox.py restates the same arithmetic.
 __device__ __forceinline__ void box_muller(uint32_t xa, uint32_t xb, float& n0, float& n1) {
-  const float u1 = u01_f32(xa);
-  const float th = fmaf((float)(xb >> 9), 7.4901405658e-07f, -3.1415922791f);   // 2 pi (u2 - 1/2), u2 = x 2^-23 + 2^-24
+  const float u1 = fmaf((float)xa, 2.3283064365386963e-10f, 1.1641532182693481e-10f);   // 2^-32, 2^-33
+  const float th = fmaf((float)xb, 1.4629180792671596e-09f, -3.1415926528583237f);     // 2 pi 2^-32, -pi (1 - 2^-32)
   float l2, r, s, c;
   asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(u1));
   asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(l2 * -1.3862943611198906f));   // sqrt(-2 ln u1)

@@ -30,14 +30,9 @@ __device__ __forceinline__ void mma16816(float d[4], const uint32_t a[4], uint32
 }
 
 // (x, y) -> packed fp16 pair h (x in the low half) and the packed remainder m
-__device__ __forceinline__ void split2(float x, float y, uint32_t& h, uint32_t& m) {
-  const __half2 hh = __floats2half2_rn(x, y);
-  const float2 hf = __half22float2(hh);
-  const __half2 mm = __floats2half2_rn(x - hf.x, y - hf.y);
-  h = *reinterpret_cast<const uint32_t*>(&hh);
-  m = *reinterpret_cast<const uint32_t*>(&mm);
-}
-__device__ __forceinline__ float sat16(float x) { return fminf(fmaxf(x, -65000.f), 65000.f); }
+__device__ __forceinline__ void split2(float x, float y, uint32_t& h, uint32_t& m) { split_half2(x, y, h, m); }
+// values beyond the fp16 range are kept finite by the saturating conversion inside split_half2 (smct_common.cuh)
+__device__ __forceinline__ float sat16(float x) { return x; }
 
 // 8 consecutive (scaled) values -> one 16-byte h unit and one m unit
 __device__ __forceinline__ void split8(const float* x, uint4& h, uint4& m) {

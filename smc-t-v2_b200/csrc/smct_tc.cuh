@@ -159,16 +159,8 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float v[32]) {
 
 // split 4 consecutive (already scaled) fp32 values into packed fp16 h and m parts (8 bytes each)
 __device__ __forceinline__ void split4(const float x[4], uint2& h, uint2& m) {
-  __half hb[4], mb[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    hb[i] = __float2half_rn(x[i]);
-    mb[i] = __float2half_rn(x[i] - __half2float(hb[i]));
-  }
-  h.x = (uint32_t)__half_as_ushort(hb[0]) | ((uint32_t)__half_as_ushort(hb[1]) << 16);
-  h.y = (uint32_t)__half_as_ushort(hb[2]) | ((uint32_t)__half_as_ushort(hb[3]) << 16);
-  m.x = (uint32_t)__half_as_ushort(mb[0]) | ((uint32_t)__half_as_ushort(mb[1]) << 16);
-  m.y = (uint32_t)__half_as_ushort(mb[2]) | ((uint32_t)__half_as_ushort(mb[3]) << 16);
+  split_half2(x[0], x[1], h.x, m.x);
+  split_half2(x[2], x[3], h.y, m.y);
 }
 
 // write 4 consecutive k-values (k0 % 4 == 0) of row r into an A operand tile (h part at base, m part at base + A_PART_BYTES)
