@@ -301,7 +301,8 @@ __global__ void __launch_bounds__(F2NT, 2) fused2_forward_kernel(const FusedArgs
     sm.bz[i] = a.p.bz[i]; sm.b2[i] = a.p.b2[i];
     sm.ln1g[i] = a.p.ln1_g[i]; sm.ln1b[i] = a.p.ln1_b[i]; sm.ln2g[i] = a.p.ln2_g[i]; sm.ln2b[i] = a.p.ln2_b[i];
   }
-  for (int i = tid; i < a.dff; i += F2NT) sm.b1[i] = a.p.b1[i];
+  // b1 is kept pre-multiplied by the operand scale s_h (a power of two, so relu(x a + b) s_h == relu(x (a s_h) + b s_h) bit for bit)
+  for (int i = tid; i < a.dff; i += F2NT) sm.b1[i] = a.p.b1[i] * reinterpret_cast<const TcHeader*>(hdr_g)->s_h;
   for (int i = tid; i < FD * Fy; i += F2NT) sm.Wo[i] = a.p.Wo[i];
   if (tid < 8) sm.sig[tid] = sigtab[(tid < 4 ? tid : (tid < 6 ? 4 + 2 * (tid - 4) + 1 : 0)) * FD];   // std k,q,v,z ; ivar q, ivar z
   if (tid == 0) sm.hdr = *reinterpret_cast<const TcHeader*>(hdr_g);
@@ -686,13 +687,13 @@ __global__ void __launch_bounds__(F2NT, 2) fused2_forward_kernel(const FusedArgs
           __syncwarp();
         }
         tc::tmem_ld32(tD_h0 + 64 * (c & 1) + tlane + n0, val);
-        const float hscale = sm.hdr.inv_o * sm.hdr.inv_w1;
+        const float hscale = sm.hdr.inv_o * sm.hdr.inv_w1 * sm.hdr.s_h;   // (sm.b1 holds b1 s_h)
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
           float cb1[4];
           ld4(&sm.b1[c * FD + n0 + 4 * j4], cb1);
 #pragma unroll
-          for (int e = 0; e < 4; ++e) val[4 * j4 + e] = fmaxf(fmaf(val[4 * j4 + e], hscale, cb1[e]), 0.f) * sm.hdr.s_h;
+          for (int e = 0; e < 4; ++e) val[4 * j4 + e] = fmaxf(fmaf(val[4 * j4 + e], hscale, cb1[e]), 0.f);
         }
 #pragma unroll
         for (int g8 = 0; g8 < 4; ++g8) tc::store_a8(sm.ZH, er, n0 + 8 * g8, &val[8 * g8]);

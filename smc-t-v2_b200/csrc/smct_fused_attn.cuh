@@ -50,7 +50,7 @@ __device__ __forceinline__ float ex2f(float x) {
 
 // L2 prefetch of the split K and V rows of one column (2 x 256 B), issued by the lane that opens the column
 __device__ __forceinline__ void prefetch_column(const unsigned char* Ks, const unsigned char* Vs, int slot, int row, int P) {
-  const size_t off = ((size_t)slot * P + row) << 8;
+  const uint32_t off = ((uint32_t)slot * (uint32_t)P + (uint32_t)row) << 8;   // < 2^32: S P 256 with S <= 4096, P <= 1024
   asm volatile("prefetch.global.L2 [%0];" ::"l"(Ks + off));
   asm volatile("prefetch.global.L2 [%0];" ::"l"(Ks + off + 128));
   asm volatile("prefetch.global.L2 [%0];" ::"l"(Vs + off));
@@ -75,18 +75,18 @@ __device__ __forceinline__ void process_group(State& st, const uint2* cd, int nc
   const uint2 d0 = cd[0];
   if ((lane & 15) >= ncols) { d.x = d0.x; d.y = 0u; }   // unused column: a valid address, an empty owner range
   __syncwarp();
+  // byte offset of the column's split rows inside this sequence's tables, computed once by the lane that holds the
+  // descriptor and passed around as a 32-bit word (S P 256 < 2^32): the 6 row pointers of a lane are base + offset
+  const uint32_t coff = ((d.x >> 16) * (uint32_t)P + (d.x & 0xFFFFu)) << 8;
   // V rows of columns 2c, 2c+1, 2c+8, 2c+9 (dims 8r .. 8r+7)
   const unsigned char* vp[4];
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const uint32_t rs = __shfl_sync(SMCT_FULL_MASK, d.x, 2 * c + (k & 1) + 8 * (k >> 1));
-    vp[k] = Vs + (((size_t)(rs >> 16) * P + (rs & 0xFFFFu)) << 8) + 16 * r;
-  }
+  for (int k = 0; k < 4; ++k)
+    vp[k] = Vs + (__shfl_sync(SMCT_FULL_MASK, coff, 2 * c + (k & 1) + 8 * (k >> 1)) + 16u * (uint32_t)r);
   float S[2][4];
 #pragma unroll
   for (int nt = 0; nt < 2; ++nt) {
-    const uint32_t rs = __shfl_sync(SMCT_FULL_MASK, d.x, 8 * nt + r);
-    const unsigned char* kp = Ks + (((size_t)(rs >> 16) * P + (rs & 0xFFFFu)) << 8) + 16 * c;
+    const unsigned char* kp = Ks + (__shfl_sync(SMCT_FULL_MASK, coff, 8 * nt + r) + 16u * (uint32_t)c);
     const uint4 h0 = *reinterpret_cast<const uint4*>(kp);
     const uint4 h1 = *reinterpret_cast<const uint4*>(kp + 64);
     const uint4 m0 = *reinterpret_cast<const uint4*>(kp + 128);

@@ -107,20 +107,23 @@ __device__ __forceinline__ void mbar_init(uint64_t* mbar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(mbar)), "r"(count) : "memory");
 }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-// bounded wait: traps instead of hanging the GPU if the MMA never commits
+// bounded wait: traps instead of hanging the GPU if the MMA never commits.  try_wait carries a suspend-time hint
+// (20 us): the warp sleeps in hardware until the phase completes instead of coming back every few hundred cycles — the
+// spin loop was 17.6 % of all executed warp-instructions of the fused forward (profiles/r02_fused2_summary.md), issue
+// slots taken from the co-resident CTA.
 __device__ __forceinline__ void mbar_wait(uint64_t* mbar, uint32_t parity) {
   const uint32_t addr = smem_u32(mbar);
   uint32_t done = 0;
 #pragma unroll 1   // (the compiler otherwise unrolls the spin loop 32 times at every wait site)
-  for (uint32_t spin = 0; spin < (1u << 22); ++spin) {
+  for (uint32_t spin = 0; spin < (1u << 20); ++spin) {
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t"
         "}\n"
         : "=r"(done)
-        : "r"(addr), "r"(parity)
+        : "r"(addr), "r"(parity), "r"(20000u)
         : "memory");
     if (done) return;
   }
