@@ -529,10 +529,11 @@ __global__ void __launch_bounds__(FNT, 1) fused_forward_kernel(const FusedArgs a
 // noise_K = K - wk(X), noise_V = V - wv(X) and the loss sums — one pass over the state instead of two.
 //
 // A pure 3 x (B,P,S,64) fp32 write stream (29.8 GB per 296 C4 sequences; a plain fill of that size takes 4.0 ms on this
-// part), so the kernel is built for memory-level parallelism: one CTA walks MAT_PB logical particles of one sequence; a
-// half-warp (16 lanes x float4) owns 8 consecutive rows of a particle, reads their 8 ancestry entries as ONE 16-byte
-// word (requested one particle ahead), and keeps 12 independent row loads in flight per thread before the first
-// store.  The output-layer dot products of 4 rows are reduced with a 5-shuffle transpose instead of 16 shuffles.
+// part), so the kernel is built to be that stream and little else: one CTA walks MAT_PB logical particles of one sequence
+// (neighbours in genealogy order); a half-warp (16 lanes x float4) owns 4 consecutive rows, reads their 4 ancestry
+// entries as one 8-byte word (requested one particle ahead), keeps the physical rows of the previous particle in
+// registers and reloads only where the ancestor changed (old slots are shared by almost all neighbours).  The
+// output-layer dot products of 4 rows are reduced with a 5-shuffle transpose instead of 16 shuffles.
 // (The first version handled one row per loop trip behind a pos -> ancestry -> row dependency chain: 7.7 ms, long
 // scoreboard 9 warps per issue slot, profiles/r02_materialize_summary.md.)
 // ------------------------------------------------------------------------------------------
@@ -548,7 +549,7 @@ struct MatArgs {
   double* loss_sums;         // [0] K, [2] V, [4] sum (y - pred_resampl)^2
 };
 
-constexpr int MAT_PB = 4;    // logical particles per CTA
+constexpr int MAT_PB = 8;    // logical particles per CTA (consecutive in genealogy order: they share most old ancestors)
 
 __device__ __forceinline__ float4 sub4(const float4 x, const float4 y) {
   return make_float4(x.x - y.x, x.y - y.y, x.z - y.z, x.w - y.w);
@@ -556,17 +557,21 @@ __device__ __forceinline__ float4 sub4(const float4 x, const float4 y) {
 
 __global__ void __launch_bounds__(256, 2) materialize_final_kernel(const MatArgs a) {
   __shared__ double red[3][8];
+  __shared__ int lp[MAT_PB];                   // logical particle at genealogy position q0 + i
   const int pblocks = (a.P + MAT_PB - 1) / MAT_PB;
   const int b = (int)(blockIdx.x / pblocks);
-  const int p0 = (int)(blockIdx.x % pblocks) * MAT_PB;
-  const int pn = min(MAT_PB, a.P - p0);
+  const int q0 = (int)(blockIdx.x % pblocks) * MAT_PB;   // the CTA owns MAT_PB consecutive POSITIONS of the genealogy order
+  const int pn = min(MAT_PB, a.P - q0);
   const int tid = threadIdx.x, c4 = tid & 15, g = tid >> 4, lane = tid & 31, wid = tid >> 5;
   const unsigned hmask = (lane & 16) ? 0xFFFF0000u : 0x0000FFFFu;   // shuffles stay inside the half-warp
   const int Fy = a.Fy, S = a.S, P = a.P;
   const unsigned short* const Ab = (a.aflag[b] ? a.A0 : a.A1) + (long long)b * P * a.Sa;
-  const unsigned short* const posb = a.pos + (long long)b * P;
-  const int npass = (S + 127) >> 7;            // 128 rows per pass: half-warp g owns rows 128 pass + 8 g .. + 7
-  const int nit = pn * npass;
+  for (int p = threadIdx.x; p < P; p += 256) {   // invert pos (logical -> position) for the CTA's positions
+    const int q = (int)a.pos[(long long)b * P + p] - q0;
+    if (q >= 0 && q < pn) lp[q] = p;
+  }
+  __syncthreads();
+  const int npass = (S + 63) >> 6;             // 64 rows per pass: half-warp g owns rows 64 pass + 4 g .. + 3
   float ivk[4], ivv[4];
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
@@ -574,43 +579,45 @@ __global__ void __launch_bounds__(256, 2) materialize_final_kernel(const MatArgs
     ivk[e] = a.kx ? expf(-a.logvar_k[d]) : 0.f;
     ivv[e] = a.kx ? expf(-a.logvar_v[d]) : 0.f;
   }
-  // ancestry entries of (iteration it) = (particle it / npass, pass it % npass); Sa is a multiple of 8 and s0 < S <= Sa
-  auto load_anc = [&](int it) -> uint4 {
-    const int pi = it / npass, s0 = ((it - pi * npass) << 7) + 8 * g;
-    if (it >= nit || s0 >= S) return make_uint4(0u, 0u, 0u, 0u);
-    const int q = posb[p0 + pi];
-    return *reinterpret_cast<const uint4*>(Ab + (long long)q * a.Sa + s0);
-  };
+  const bool up8 = (c4 & 8) != 0, up4 = (c4 & 4) != 0;
+  const int jr = (up8 ? 2 : 0) + (up4 ? 1 : 0);   // the row of the half-warp's 4 this lane ends up with after the transpose-reduce
   float lk = 0.f, lv = 0.f, ly = 0.f;
-  uint4 av_next = load_anc(0);
-  for (int it = 0; it < nit; ++it) {
-    const uint4 av = av_next;
-    av_next = load_anc(it + 1);
-    const int pi = it / npass, s0 = ((it - pi * npass) << 7) + 8 * g;
-    const long long bp = (long long)b * P + p0 + pi;
-    const uint32_t aw[4] = {av.x, av.y, av.z, av.w};
+  for (int pass = 0; pass < npass; ++pass) {
+    const int sb = (pass << 6) + 4 * g;
+    if (sb >= S) continue;                      // (no barrier inside the loop; Sa is a multiple of 8, so sb + 3 < Sa)
+    // 4 ancestry entries of particle pi as one 8-byte word, requested one particle ahead
+    auto load_anc = [&](int pi) -> uint2 {
+      if (pi >= pn) return make_uint2(0u, 0u);
+      return *reinterpret_cast<const uint2*>(Ab + (long long)(q0 + pi) * a.Sa + sb);
+    };
+    // The CTA's particles are neighbours in genealogy order: at old slots they mostly descend from the same physical row.
+    // Each half-warp keeps the rows it loaded for the previous particle and reloads only where the ancestor changed, so
+    // the pass is a write stream with a thin read stream beside it.
+    float4 k4[4], v4[4], r4[4];
+    uint32_t have[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      const int sb = s0 + 4 * half;
-      float4 k4[4], v4[4], r4[4];
+    for (int j = 0; j < 4; ++j) k4[j] = v4[j] = r4[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    uint2 av_next = load_anc(0);
+    for (int pi = 0; pi < pn; ++pi) {
+      const uint2 av = av_next;
+      av_next = load_anc(pi + 1);
+      const long long bp = (long long)b * P + lp[pi];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const int s = sb + j;
-        const uint32_t w = aw[2 * half + (j >> 1)];
-        const int row = (j & 1) ? (int)(w >> 16) : (int)(w & 0xFFFFu);
-        k4[j] = v4[j] = r4[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (s < S) {
-          const long long src = (((long long)b * S + s) * P + row) * FD + 4 * c4;
+        const uint32_t w = (j >> 1) ? av.y : av.x;
+        const uint32_t row = (j & 1) ? (w >> 16) : (w & 0xFFFFu);
+        if (sb + j < S && row != have[j]) {
+          const long long src = (((long long)b * S + sb + j) * P + row) * FD + 4 * c4;
           k4[j] = *reinterpret_cast<const float4*>(a.Kp + src);
           v4[j] = *reinterpret_cast<const float4*>(a.Vp + src);
           r4[j] = *reinterpret_cast<const float4*>(a.Rp + src);
+          have[j] = row;
         }
       }
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const int s = sb + j;
-        if (s < S) {
-          const long long dst = (bp * S + s) * FD + 4 * c4;
+        if (sb + j < S) {
+          const long long dst = (bp * S + sb + j) * FD + 4 * c4;
           __stcs(reinterpret_cast<float4*>(a.K + dst), k4[j]);   // streaming stores: the materialised state is not read again
           __stcs(reinterpret_cast<float4*>(a.V + dst), v4[j]);   // by the forward and should not evict the shared source rows
           __stcs(reinterpret_cast<float4*>(a.R + dst), r4[j]);
@@ -619,10 +626,9 @@ __global__ void __launch_bounds__(256, 2) materialize_final_kernel(const MatArgs
       if (a.kx) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const int s = sb + j;
-          if (s < S) {
-            const long long xs = ((long long)b * S + s) * FD + 4 * c4;
-            const long long dst = (bp * S + s) * FD + 4 * c4;
+          if (sb + j < S) {
+            const long long xs = ((long long)b * S + sb + j) * FD + 4 * c4;
+            const long long dst = (bp * S + sb + j) * FD + 4 * c4;
             const float4 nk = sub4(k4[j], *reinterpret_cast<const float4*>(a.kx + xs));
             const float4 nv = sub4(v4[j], *reinterpret_cast<const float4*>(a.vx + xs));
             if (a.noise_K) *reinterpret_cast<float4*>(a.noise_K + dst) = nk;
@@ -635,8 +641,6 @@ __global__ void __launch_bounds__(256, 2) materialize_final_kernel(const MatArgs
       if (a.pred_resampl || a.y) {
         // the half-warp's 4 rows x Fy outputs: per-lane partial dot products, then a transpose-reduce over the 16 lanes
         // (xor 8: 4 -> 2 values, xor 4: 2 -> 1, xor 2, xor 1); lane l ends with row 2 bit3(l) + bit2(l)
-        const bool up8 = (c4 & 8) != 0, up4 = (c4 & 4) != 0;
-        const int jr = (up8 ? 2 : 0) + (up4 ? 1 : 0);
         const int s = sb + jr;
         for (int f = 0; f < Fy; ++f) {
           const float* w = a.Wo + (4 * c4) * Fy + f;
