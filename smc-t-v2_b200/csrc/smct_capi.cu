@@ -14,6 +14,7 @@
 #include "smct_staged.cuh"
 #include "smct_small.cuh"
 #include "smct_fused.cuh"
+#include "smct_materialize.cuh"
 #include "smct_tc.cuh"
 #include "smct_fused_tc.cuh"
 #include "smct_fused2.cuh"
@@ -480,7 +481,14 @@ int forward_fused(const smct_shape& s, const smct_params& pr, const smct_io& io,
   m.y = io.loss_sums ? (const float*)io.y : nullptr;
   m.K = io.K; m.V = io.V; m.R = io.R;
   m.pred_resampl = io.pred_resampl; m.noise_K = io.noise_K; m.noise_V = io.noise_V; m.loss_sums = io.loss_sums;
-  smct::materialize_final_kernel<<<(unsigned)((long long)B * ((P + smct::MAT_PB - 1) / smct::MAT_PB)), 256, 0, st>>>(m);
+  {
+    static PerDeviceOnce mat_once;
+    const size_t mat_smem = sizeof(smct::MatSmem) + 128;
+    if (mat_once.need())
+      SMCT_CUDA(cudaFuncSetAttribute(smct::materialize_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mat_smem));
+    const unsigned grid = (unsigned)((long long)B * ((P + smct::MAT_PB - 1) / smct::MAT_PB) * ((S + smct::MAT_ROWS - 1) / smct::MAT_ROWS));
+    smct::materialize_final_kernel<<<grid, smct::MAT_NT, mat_smem, st>>>(m);
+  }
   SMCT_LAUNCH_CHECK("materialize_final_kernel");
   return SMCT_OK;
 }

@@ -524,161 +524,6 @@ __global__ void __launch_bounds__(FNT, 1) fused_forward_kernel(const FusedArgs a
 }
 
 // ------------------------------------------------------------------------------------------
-// materialize_final_kernel: K,V,R (B,P,S,64) <- slot-major physical rows through the final ancestry table,
-// fused with the output heads of SMC_Transformer.call (SMC_Transformer.py:231-236): pred_resampl = R·Wo,
-// noise_K = K - wk(X), noise_V = V - wv(X) and the loss sums — one pass over the state instead of two.
-//
-// A pure 3 x (B,P,S,64) fp32 write stream (29.8 GB per 296 C4 sequences; a plain fill of that size takes 4.0 ms on this
-// part), so the kernel is built to be that stream and little else: one CTA walks MAT_PB logical particles of one sequence
-// (neighbours in genealogy order); a half-warp (16 lanes x float4) owns 4 consecutive rows, reads their 4 ancestry
-// entries as one 8-byte word (requested one particle ahead), keeps the physical rows of the previous particle in
-// registers and reloads only where the ancestor changed (old slots are shared by almost all neighbours).  The
-// output-layer dot products of 4 rows are reduced with a 5-shuffle transpose instead of 16 shuffles.
-// (The first version handled one row per loop trip behind a pos -> ancestry -> row dependency chain: 7.7 ms, long
-// scoreboard 9 warps per issue slot, profiles/r02_materialize_summary.md.)
-// ------------------------------------------------------------------------------------------
-struct MatArgs {
-  int B, P, S, Sa, Fy, logvar_dim;
-  const float *Kp, *Vp, *Rp;
-  const unsigned short *A0, *A1, *pos;
-  const int* aflag;
-  const float *kx, *vx, *Wo, *logvar_k, *logvar_v;
-  const float* y;            // (B,S,Fy) or null
-  float *K, *V, *R;
-  float *pred_resampl, *noise_K, *noise_V;
-  double* loss_sums;         // [0] K, [2] V, [4] sum (y - pred_resampl)^2
-};
-
-constexpr int MAT_PB = 8;    // logical particles per CTA (consecutive in genealogy order: they share most old ancestors)
-
-__device__ __forceinline__ float4 sub4(const float4 x, const float4 y) {
-  return make_float4(x.x - y.x, x.y - y.y, x.z - y.z, x.w - y.w);
-}
-
-__global__ void __launch_bounds__(256, 2) materialize_final_kernel(const MatArgs a) {
-  __shared__ double red[3][8];
-  __shared__ int lp[MAT_PB];                   // logical particle at genealogy position q0 + i
-  const int pblocks = (a.P + MAT_PB - 1) / MAT_PB;
-  const int b = (int)(blockIdx.x / pblocks);
-  const int q0 = (int)(blockIdx.x % pblocks) * MAT_PB;   // the CTA owns MAT_PB consecutive POSITIONS of the genealogy order
-  const int pn = min(MAT_PB, a.P - q0);
-  const int tid = threadIdx.x, c4 = tid & 15, g = tid >> 4, lane = tid & 31, wid = tid >> 5;
-  const unsigned hmask = (lane & 16) ? 0xFFFF0000u : 0x0000FFFFu;   // shuffles stay inside the half-warp
-  const int Fy = a.Fy, S = a.S, P = a.P;
-  const unsigned short* const Ab = (a.aflag[b] ? a.A0 : a.A1) + (long long)b * P * a.Sa;
-  for (int p = threadIdx.x; p < P; p += 256) {   // invert pos (logical -> position) for the CTA's positions
-    const int q = (int)a.pos[(long long)b * P + p] - q0;
-    if (q >= 0 && q < pn) lp[q] = p;
-  }
-  __syncthreads();
-  const int npass = (S + 63) >> 6;             // 64 rows per pass: half-warp g owns rows 64 pass + 4 g .. + 3
-  float ivk[4], ivv[4];
-#pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    const int d = a.logvar_dim > 1 ? (4 * c4 + e) : 0;
-    ivk[e] = a.kx ? expf(-a.logvar_k[d]) : 0.f;
-    ivv[e] = a.kx ? expf(-a.logvar_v[d]) : 0.f;
-  }
-  const bool up8 = (c4 & 8) != 0, up4 = (c4 & 4) != 0;
-  const int jr = (up8 ? 2 : 0) + (up4 ? 1 : 0);   // the row of the half-warp's 4 this lane ends up with after the transpose-reduce
-  float lk = 0.f, lv = 0.f, ly = 0.f;
-  for (int pass = 0; pass < npass; ++pass) {
-    const int sb = (pass << 6) + 4 * g;
-    if (sb >= S) continue;                      // (no barrier inside the loop; Sa is a multiple of 8, so sb + 3 < Sa)
-    // 4 ancestry entries of particle pi as one 8-byte word, requested one particle ahead
-    auto load_anc = [&](int pi) -> uint2 {
-      if (pi >= pn) return make_uint2(0u, 0u);
-      return *reinterpret_cast<const uint2*>(Ab + (long long)(q0 + pi) * a.Sa + sb);
-    };
-    // The CTA's particles are neighbours in genealogy order: at old slots they mostly descend from the same physical row.
-    // Each half-warp keeps the rows it loaded for the previous particle and reloads only where the ancestor changed, so
-    // the pass is a write stream with a thin read stream beside it.
-    float4 k4[4], v4[4], r4[4];
-    uint32_t have[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
-#pragma unroll
-    for (int j = 0; j < 4; ++j) k4[j] = v4[j] = r4[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-    uint2 av_next = load_anc(0);
-    for (int pi = 0; pi < pn; ++pi) {
-      const uint2 av = av_next;
-      av_next = load_anc(pi + 1);
-      const long long bp = (long long)b * P + lp[pi];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const uint32_t w = (j >> 1) ? av.y : av.x;
-        const uint32_t row = (j & 1) ? (w >> 16) : (w & 0xFFFFu);
-        if (sb + j < S && row != have[j]) {
-          const long long src = (((long long)b * S + sb + j) * P + row) * FD + 4 * c4;
-          k4[j] = *reinterpret_cast<const float4*>(a.Kp + src);
-          v4[j] = *reinterpret_cast<const float4*>(a.Vp + src);
-          r4[j] = *reinterpret_cast<const float4*>(a.Rp + src);
-          have[j] = row;
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if (sb + j < S) {
-          const long long dst = (bp * S + sb + j) * FD + 4 * c4;
-          __stcs(reinterpret_cast<float4*>(a.K + dst), k4[j]);   // streaming stores: the materialised state is not read again
-          __stcs(reinterpret_cast<float4*>(a.V + dst), v4[j]);   // by the forward and should not evict the shared source rows
-          __stcs(reinterpret_cast<float4*>(a.R + dst), r4[j]);
-        }
-      }
-      if (a.kx) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if (sb + j < S) {
-            const long long xs = ((long long)b * S + sb + j) * FD + 4 * c4;
-            const long long dst = (bp * S + sb + j) * FD + 4 * c4;
-            const float4 nk = sub4(k4[j], *reinterpret_cast<const float4*>(a.kx + xs));
-            const float4 nv = sub4(v4[j], *reinterpret_cast<const float4*>(a.vx + xs));
-            if (a.noise_K) *reinterpret_cast<float4*>(a.noise_K + dst) = nk;
-            if (a.noise_V) *reinterpret_cast<float4*>(a.noise_V + dst) = nv;
-            lk = fmaf(nk.x * nk.x, ivk[0], fmaf(nk.y * nk.y, ivk[1], fmaf(nk.z * nk.z, ivk[2], fmaf(nk.w * nk.w, ivk[3], lk))));
-            lv = fmaf(nv.x * nv.x, ivv[0], fmaf(nv.y * nv.y, ivv[1], fmaf(nv.z * nv.z, ivv[2], fmaf(nv.w * nv.w, ivv[3], lv))));
-          }
-        }
-      }
-      if (a.pred_resampl || a.y) {
-        // the half-warp's 4 rows x Fy outputs: per-lane partial dot products, then a transpose-reduce over the 16 lanes
-        // (xor 8: 4 -> 2 values, xor 4: 2 -> 1, xor 2, xor 1); lane l ends with row 2 bit3(l) + bit2(l)
-        const int s = sb + jr;
-        for (int f = 0; f < Fy; ++f) {
-          const float* w = a.Wo + (4 * c4) * Fy + f;
-          const float w0 = __ldg(w), w1 = __ldg(w + Fy), w2 = __ldg(w + 2 * Fy), w3 = __ldg(w + 3 * Fy);
-          float pt[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) pt[j] = fmaf(r4[j].x, w0, fmaf(r4[j].y, w1, fmaf(r4[j].z, w2, r4[j].w * w3)));
-          const float q0 = (up8 ? pt[2] : pt[0]) + __shfl_xor_sync(hmask, up8 ? pt[0] : pt[2], 8);
-          const float q1 = (up8 ? pt[3] : pt[1]) + __shfl_xor_sync(hmask, up8 ? pt[1] : pt[3], 8);
-          float part = (up4 ? q1 : q0) + __shfl_xor_sync(hmask, up4 ? q0 : q1, 4);
-          part += __shfl_xor_sync(hmask, part, 2);
-          part += __shfl_xor_sync(hmask, part, 1);
-          if ((c4 & 3) == 0 && s < S) {
-            if (a.pred_resampl) a.pred_resampl[(bp * S + s) * Fy + f] = part;
-            if (a.y) {
-              const float diff = a.y[((long long)b * S + s) * Fy + f] - part;
-              ly = fmaf(diff, diff, ly);
-            }
-          }
-        }
-      }
-    }
-  }
-  if (a.loss_sums) {
-    lk = warp_sum(lk); lv = warp_sum(lv); ly = warp_sum(ly);
-    if (lane == 0) { red[0][wid] = lk; red[1][wid] = lv; red[2][wid] = ly; }
-    __syncthreads();
-    if (tid == 0) {
-      double s0 = 0, s1 = 0, s2 = 0;
-      for (int i = 0; i < 8; ++i) { s0 += red[0][i]; s1 += red[1][i]; s2 += red[2][i]; }
-      atomicAdd(a.loss_sums + 0, s0);
-      atomicAdd(a.loss_sums + 2, s1);
-      atomicAdd(a.loss_sums + 4, s2);
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
 inline size_t fused_align(size_t x) { return (x + 255) / 256 * 256; }
