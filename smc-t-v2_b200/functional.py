@@ -168,8 +168,8 @@ def forward(shape: SmctShape, params: Dict[str, torch.Tensor], x_in: torch.Tenso
         raise ValueError("eps must have shape (4,S,B,P,D)")
     if eps is not None and shape.D == 64 and shape.algo in (ALGO["auto"], ALGO["fused"], ALGO["fused_v1"]):
         # the fp16-split tensor-core operands of the fused forward are scaled from analytic bounds |LN1(x) W + b| + 16 sigma
-        # (smct_tc.cuh); the device generator cannot exceed 5.8 sigma, injected draws are checked here, so the +-65000
-        # operand clamps are provably dead
+        # (smct_tc.cuh); the device generator cannot exceed 6.8 sigma, injected draws are checked here, so the saturating
+        # fp16 conversions of the operands never saturate
         if float(eps.abs().max()) > 16.0:
             raise ValueError("injected eps exceeds 16 standard deviations: outside the operand scaling of the fused forward")
     if u is not None and tuple(u.shape) != (S, B, P):
