@@ -107,7 +107,7 @@ typedef struct smct_io {
   uint64_t seed;
   float *pred;             /* (B,P,S,F_y)  output_layer(R unresampled) */
   float *pred_resampl;     /* (B,P,S,F_y)  output_layer(R resampled) */
-  float *K, *V, *R;        /* (B,P,S,D)    final resampled states */
+  float *K, *V, *R;        /* (B,P,S,D)    final resampled states; 16-byte aligned (128-bit stores / bulk copies) */
   float *w;                /* (B,P,S)      filtering weights (gaussian: normalised; classification: raw) */
   int32_t *i_out;          /* optional (S,B,P) drawn ancestor indices */
   float *logw;             /* optional (S,B,P) unnormalised log-weights (gaussian) / w (classification) */

@@ -2,6 +2,7 @@
 // Host-side argument checking, workspace carving and kernel launches.  No CPU fallback.
 #include <cuda_runtime.h>
 #include <stdarg.h>
+#include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -601,6 +602,8 @@ int smct_forward(const smct_shape* shape, const smct_params* params, const smct_
   if (int rc = check_shape(shape)) return rc;
   if (!params || !io) return fail(SMCT_ERR_INVALID, "params/io is NULL");
   if (!io->x_in || !io->K || !io->V || !io->R) return fail(SMCT_ERR_INVALID, "x_in, K, V, R are required");
+  if ((((uintptr_t)io->K | (uintptr_t)io->V | (uintptr_t)io->R) & 15u) != 0)   // 128-bit stores and bulk copies
+    return fail(SMCT_ERR_INVALID, "K, V, R must be 16-byte aligned");
   if (shape->noise_on && !io->y) return fail(SMCT_ERR_INVALID, "y (targets) required when noise is on");
   if (!workspace) return fail(SMCT_ERR_WORKSPACE, "workspace is NULL");
   cudaStream_t st = (cudaStream_t)stream;

@@ -265,6 +265,20 @@ def test_auto_algo_selects_fused_and_rejects_unsupported():
         util.run_device(cfg, p, x_in, y, eps, u, algo="fused")   # d_model 8 is not served by the fused kernel
 
 
+def test_forward_rejects_misaligned_state_buffers():
+    """K, V, R are written with 128-bit stores / bulk copies: a caller buffer that is not 16-byte aligned is an error,
+    not a misaligned-address fault."""
+    from smct_b200 import _lib
+    B, P, S, D = 2, 16, 8, 64
+    shape = F.make_shape(B, P, S, D, dff=64, F_x=1, F_y=1, algo="auto")
+    from smct_b200 import utils
+    params = {k: torch.as_tensor(v, device="cuda") for k, v in utils.init_parameters(D, 64, 1, 1).items()}
+    x = torch.zeros(B, S, 1, device="cuda")
+    base = torch.empty(B * P * S * D + 1, device="cuda")
+    with pytest.raises(_lib.SmctError, match="16-byte aligned"):
+        F.forward(shape, params, x, x, seed=1, out={"K": base[1:].view(B, P, S, D)})
+
+
 def test_forward_device_rng_matches_oracle_with_same_draws():
     """Throughput mode (Philox on device): read the very same draws back through smct_fill_* and
     inject them into the oracle."""
