@@ -53,6 +53,7 @@ struct BwdArgs {
   const float* classic_w;                 // optional (B,S): weight of the classic-loss term of row (b,s) (masked losses)
   smct_params p;
   const float *WzT, *W1T, *W2T;           // transposed weights
+  const float *WqT, *WkT, *WvT;           // (out,in): thread d of bwd_rows walks column d — coalesced
   const float *K, *V;                     // (B,P,S,D) final states
   const int* i_out;                       // (S,B,P)
   unsigned short* anc;                    // (B,S,P) logical ancestor of final particle p at slot s
@@ -61,6 +62,7 @@ struct BwdArgs {
   const int* node_bs;                     // (N) b*S+s
   const unsigned short *node_p, *node_L;  // (N) representative final particle, logical ancestor id
   const float* node_m;                    // (N) multiplicity
+  unsigned short* node_of;                // (B,P,S) index inside its (b,s) segment of the node whose representative is p (0xFFFF: none)
   float *Zm, *dZm, *stat;                 // (N,D), (N,D), (N,2) per node
   float* Qm;                              // (N,D) q row of the node (k_, noise regenerated once by bwd_attn_fwd)
   float *dq_sum, *dk_sum, *dv_sum, *dxln_sum, *dkx_sum, *dvx_sum;   // (B,S,D)
@@ -132,9 +134,12 @@ __global__ void __launch_bounds__(1024) node_scan_kernel(int n, const int* cnt, 
   if (tid == 1023) off[n] = part[1023];
 }
 
-__global__ void __launch_bounds__(256) node_fill_kernel(int P, const unsigned short* anc, const int* node_off,
+// node_of (optional, pre-filled with 0xFFFF): node_of[b][rep][s] = index of the node inside its (b,s) segment.  The
+// representative (smallest final particle below the node) can only decrease towards the root, so the nodes represented
+// by one particle are a chain of consecutive slots [s_top, S-1] on that particle's lineage.
+__global__ void __launch_bounds__(256) node_fill_kernel(int P, int S, const unsigned short* anc, const int* node_off,
                                                         int* node_bs, unsigned short* node_p, unsigned short* node_L,
-                                                        float* node_m) {
+                                                        float* node_m, unsigned short* node_of) {
   extern __shared__ int nsm[];
   __shared__ int scratch[8];
   __shared__ int wbase[9];
@@ -142,7 +147,9 @@ __global__ void __launch_bounds__(256) node_fill_kernel(int P, const unsigned sh
   int* rep = nsm + P;
   node_histogram(P, anc + (long long)blockIdx.x * P, cnt, rep, scratch);
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  int base = node_off[blockIdx.x];
+  const int seg0 = node_off[blockIdx.x];
+  const int b_ = blockIdx.x / S, s_ = blockIdx.x % S;
+  int base = seg0;
   for (int i0 = 0; i0 < P; i0 += 256) {      // ordered compaction, 256 ancestors per pass
     const int i = i0 + tid;
     const bool live = (i < P) && (cnt[i] > 0);
@@ -158,6 +165,7 @@ __global__ void __launch_bounds__(256) node_fill_kernel(int P, const unsigned sh
       node_p[u] = (unsigned short)rep[i];
       node_L[u] = (unsigned short)i;
       node_m[u] = (float)cnt[i];
+      if (node_of) node_of[((long long)b_ * P + rep[i]) * S + s_] = (unsigned short)(u - seg0);
     }
     base += wbase[8];
   }
@@ -826,6 +834,139 @@ __global__ void __launch_bounds__(BWD_ANT) bwd_attn_bwd_half_kernel(const BwdArg
 }
 
 // ------------------------------------------------------------------------------------------
+// attention backward over CHAINS (d_model a multiple of 4, <= 64): the same arithmetic and work split as the half-warp
+// form below, but the nodes are walked by representative particle.  All nodes represented by particle p lie on p's
+// lineage, so they attend over the SAME rows K[b,p,0..s], V[b,p,0..s]: a half-warp loads the rows of its target slots
+// once per chain and keeps them in registers for every node of the chain.  The half-warp form reloaded 512 B per
+// (node, slot) pair (27 GB of DRAM reads per 296 C4 sequences, 59 % of its stall samples on those loads, 17.7 ms);
+// here the K / V tensors are read once.
+// ------------------------------------------------------------------------------------------
+constexpr int BWD_CNT = 256;     // threads per CTA of the chain kernel (two or more CTAs per SM walk different chains)
+constexpr int BWD_CG = 16;       // CTAs per sequence
+
+__global__ void __launch_bounds__(BWD_CNT, 2) bwd_attn_bwd_chain_kernel(const BwdArgs a) {
+  const int D = a.D, S = a.S, P = a.P;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int l16 = lane & 15, hsel = lane >> 4;
+  constexpr int NWA = BWD_CNT / 32;
+  const int b = blockIdx.x / BWD_CG, g = blockIdx.x % BWD_CG;
+  const float inv_sqrt_d = 1.0f / sqrtf((float)D);
+  const int d0 = 4 * l16;
+  const bool okd = d0 < D;
+  float ck[4], cv[4];   // 1/sigma^2 (per dimension when logvar_dim = D) times the loss normalisation
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int li = (a.logvar_dim > 1 && okd) ? d0 + e : 0;
+    ck[e] = expf(-a.p.logvar_k[li]) * a.inv_n; cv[e] = expf(-a.p.logvar_v[li]) * a.inv_n;
+  }
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  auto ld4g = [&](const float* p) { return okd ? *reinterpret_cast<const float4*>(p + d0) : zero4; };
+  auto dot4 = [](const float4& x, const float4& y) { return fmaf(x.x, y.x, fmaf(x.y, y.y, fmaf(x.z, y.z, x.w * y.w))); };
+  auto axpy4 = [](float s_, const float4& x, float4& y) { y.x = fmaf(s_, x.x, y.x); y.y = fmaf(s_, x.y, y.y); y.z = fmaf(s_, x.z, y.z); y.w = fmaf(s_, x.w, y.w); };
+  for (int tbase = 0; tbase < S; tbase += 2 * NWA * BWD_TJ2) {
+    float4 dk[BWD_TJ2], dv[BWD_TJ2];
+#pragma unroll
+    for (int j = 0; j < BWD_TJ2; ++j) { dk[j] = zero4; dv[j] = zero4; }
+    const int t0 = tbase + 2 * wid + hsel;               // this half-warp's first target slot of the pass
+    const int s_min = tbase + 2 * wid;                   // nodes below it see none of this warp's target slots
+    for (int p = g; p < P; p += BWD_CG) {                // representatives of this CTA (strided: long and short chains mix)
+      const unsigned short* chain = a.node_of + ((long long)b * P + p) * S;
+      unsigned idx = chain[S - 1];
+      if (idx == 0xFFFFu) continue;                      // p represents no node (CTA-uniform)
+      const long long bp = (long long)b * P + p;
+      const float* Kp = a.K + bp * S * D;
+      const float* Vp = a.V + bp * S * D;
+      float4 kr[BWD_TJ2], vr[BWD_TJ2];                   // the lineage's rows at this half-warp's target slots: once per chain
+#pragma unroll
+      for (int j = 0; j < BWD_TJ2; ++j) {
+        const int t = t0 + 2 * NWA * j;
+        kr[j] = t < S ? ld4g(Kp + (long long)t * D) : zero4;
+        vr[j] = t < S ? ld4g(Vp + (long long)t * D) : zero4;
+      }
+      // the chain is the suffix [s_top, S-1]; the rows of the NEXT node are requested before the current one is worked on
+      int s = S - 1;
+      long long u = (long long)a.node_off[b * S + s] + idx;
+      float4 q = ld4g(a.Qm + u * D), dz = ld4g(a.dZm + u * D), zr = ld4g(a.Zm + u * D);
+      float2 ml = *reinterpret_cast<const float2*>(a.stat + u * 2);
+      while (true) {
+        const int bs = b * S + s;
+        // ---- request the next node of the chain ----
+        const bool more = (s > s_min) && (s > 0);
+        unsigned idx_n = 0xFFFFu;
+        if (more) idx_n = chain[s - 1];
+        const bool have_n = idx_n != 0xFFFFu;
+        long long u_n = 0;
+        float4 q_n = zero4, dz_n = zero4, zr_n = zero4;
+        float2 ml_n = make_float2(0.f, 1.f);
+        if (have_n) {
+          u_n = (long long)a.node_off[bs - 1] + idx_n;
+          q_n = ld4g(a.Qm + u_n * D); dz_n = ld4g(a.dZm + u_n * D); zr_n = ld4g(a.Zm + u_n * D);
+          ml_n = *reinterpret_cast<const float2*>(a.stat + u_n * 2);
+        }
+        // ---- the current node ----
+        if (s >= s_min) {
+          const int s_lo = (a.attn_window >= 0 && s > a.attn_window) ? s - a.attn_window : 0;
+          float4 dq = zero4;
+          const float delta = half_sum(dot4(dz, zr));      // sum_tau a_tau (dz . v_tau) = dz . z_
+          const float m = ml.x, inv_l = 1.0f / ml.y;
+#pragma unroll
+          for (int j = 0; j < BWD_TJ2; ++j) {
+            const int t = t0 + 2 * NWA * j;
+            const bool valid = (t <= s) && (t >= s_lo);    // uniform per half-warp; the shuffles are executed by all lanes
+            const float sc = half_sum(dot4(q, kr[j])) * inv_sqrt_d;
+            const float dA = half_sum(dot4(dz, vr[j]));
+            if (valid) {
+              const float at = expf(sc - m) * inv_l;
+              const float dS = at * (dA - delta) * inv_sqrt_d;
+              axpy4(dS, kr[j], dq);
+              axpy4(dS, q, dk[j]);
+              axpy4(at, dz, dv[j]);
+              if (t == s && okd) {
+                // direct terms of the loss on the resampled K/V noises of the node's own row: 1/2 ||K - kx||^2 / sigma_k^2
+                // (same for V), once per final particle that descends from the node
+                const float mult = a.node_m[u];
+                const float4 kx = *reinterpret_cast<const float4*>(a.kx + (long long)bs * D + d0);
+                const float4 vx = *reinterpret_cast<const float4*>(a.vx + (long long)bs * D + d0);
+                const float tk[4] = {mult * ck[0] * (kr[j].x - kx.x), mult * ck[1] * (kr[j].y - kx.y),
+                                     mult * ck[2] * (kr[j].z - kx.z), mult * ck[3] * (kr[j].w - kx.w)};
+                const float tv[4] = {mult * cv[0] * (vr[j].x - vx.x), mult * cv[1] * (vr[j].y - vx.y),
+                                     mult * cv[2] * (vr[j].z - vx.z), mult * cv[3] * (vr[j].w - vx.w)};
+                dk[j].x += tk[0]; dk[j].y += tk[1]; dk[j].z += tk[2]; dk[j].w += tk[3];
+                dv[j].x += tv[0]; dv[j].y += tv[1]; dv[j].z += tv[2]; dv[j].w += tv[3];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  atomicAdd(a.dkx_sum + (long long)bs * D + d0 + e, -tk[e]);
+                  atomicAdd(a.dvx_sum + (long long)bs * D + d0 + e, -tv[e]);
+                }
+              }
+            }
+          }
+          // dq of the node: the two halves worked on different slots; combine, then one native global RED per element
+          dq.x += __shfl_xor_sync(SMCT_FULL_MASK, dq.x, 16); dq.y += __shfl_xor_sync(SMCT_FULL_MASK, dq.y, 16);
+          dq.z += __shfl_xor_sync(SMCT_FULL_MASK, dq.z, 16); dq.w += __shfl_xor_sync(SMCT_FULL_MASK, dq.w, 16);
+          if (hsel == 0 && okd) {
+            float* dst = a.dq_sum + (long long)bs * D + d0;
+            atomicAdd(dst, dq.x); atomicAdd(dst + 1, dq.y); atomicAdd(dst + 2, dq.z); atomicAdd(dst + 3, dq.w);
+          }
+        }
+        if (!have_n) break;                              // warp-uniform (s_min depends on the warp only)
+        --s; u = u_n; q = q_n; dz = dz_n; zr = zr_n; ml = ml_n;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < BWD_TJ2; ++j) {
+      const int t = t0 + 2 * NWA * j;
+      if (t < S && okd) {
+        float* dkp = a.dk_sum + ((long long)b * S + t) * D + d0;
+        float* dvp = a.dv_sum + ((long long)b * S + t) * D + d0;
+        atomicAdd(dkp, dk[j].x); atomicAdd(dkp + 1, dk[j].y); atomicAdd(dkp + 2, dk[j].z); atomicAdd(dkp + 3, dk[j].w);
+        atomicAdd(dvp, dv[j].x); atomicAdd(dvp + 1, dv[j].y); atomicAdd(dvp + 2, dv[j].z); atomicAdd(dvp + 3, dv[j].w);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // shared rows (b,s): q_/k_/v_ projections of LN1(X), kx/vx projections of X, LN1 backward, input encoding
 // persistent CTAs of 128 threads, CTA-private replica
 // ------------------------------------------------------------------------------------------
@@ -842,6 +983,16 @@ __global__ void __launch_bounds__(128) bwd_rows_kernel(const BwdArgs a) {
   const int tid = threadIdx.x;
   float* rep = a.rep + (long long)blockIdx.x * a.lay.total;
   const long long nrows = (long long)a.B * S;
+  // The D x D weight gradients of the CTA's rows are accumulated in REGISTERS when the element -> thread map is the same
+  // for every row (128 % D == 0, at most 32 elements per thread and matrix): element (k, n) with n = tid % D,
+  // k = tid / D + i (128 / D).  (The first version added every row's outer products to the replica in global memory:
+  // 12 288 read-modify-writes per row, 32 us per row, 4.2 ms per 296 C4 sequences at 9 % issue activity.)
+  const bool regacc = (128 % D == 0) && (D * D <= 128 * 32);
+  const int rn = tid % D, rk0 = tid / D, rkstep = regacc ? 128 / D : 0;
+  float aq[32], ak[32], av[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) aq[i] = ak[i] = av[i] = 0.f;
+  float g_ln1g = 0.f, g_ln1b = 0.f, g_bq = 0.f, g_bk = 0.f, g_bv = 0.f;   // element d = tid of the vectors (D <= 128)
   for (long long row = blockIdx.x; row < nrows; row += gridDim.x) {
     __syncthreads();
     float s1 = 0.f;
@@ -864,8 +1015,8 @@ __global__ void __launch_bounds__(128) bwd_rows_kernel(const BwdArgs a) {
     float u1 = 0.f, u2 = 0.f;
     for (int d = tid; d < D; d += 128) {
       float acc = a.dxln_sum[row * D + d];
-      for (int n = 0; n < D; ++n)
-        acc = fmaf(dq[n], a.p.Wq[d * D + n], fmaf(dk[n], a.p.Wk[d * D + n], fmaf(dv[n], a.p.Wv[d * D + n], acc)));
+      for (int n = 0; n < D; ++n)   // (transposed copies: consecutive threads read consecutive words; W[d][n] would be 32 lines per load)
+        acc = fmaf(dq[n], a.WqT[n * D + d], fmaf(dk[n], a.WkT[n * D + d], fmaf(dv[n], a.WvT[n * D + d], acc)));
       t1[d] = acc;
       const float dxh = acc * a.p.ln1_g[d];
       u1 += dxh; u2 = fmaf(dxh, xh[d], u2);
@@ -874,20 +1025,34 @@ __global__ void __launch_bounds__(128) bwd_rows_kernel(const BwdArgs a) {
     const float m2 = block_sum(u2, scratch) / (float)D;
     for (int d = tid; d < D; d += 128) {
       float acc = rstd * (t1[d] * a.p.ln1_g[d] - m1 - xh[d] * m2);
-      for (int n = 0; n < D; ++n) acc = fmaf(dkx[n], a.p.Wk[d * D + n], fmaf(dvx[n], a.p.Wv[d * D + n], acc));
+      for (int n = 0; n < D; ++n) acc = fmaf(dkx[n], a.WkT[n * D + d], fmaf(dvx[n], a.WvT[n * D + d], acc));
       dX[d] = acc;
-      rep[a.lay.ln1_g + d] += t1[d] * xh[d];
-      rep[a.lay.ln1_b + d] += t1[d];
-      rep[a.lay.bq + d] += dq[d];
-      rep[a.lay.bk + d] += dk[d] + dkx[d];
-      rep[a.lay.bv + d] += dv[d] + dvx[d];
+      g_ln1g = fmaf(t1[d], xh[d], g_ln1g);
+      g_ln1b += t1[d];
+      g_bq += dq[d];
+      g_bk += dk[d] + dkx[d];
+      g_bv += dv[d] + dvx[d];
     }
     __syncthreads();
-    for (int idx = tid; idx < D * D; idx += 128) {
-      const int k = idx / D, n = idx - k * D;
-      rep[a.lay.Wq + idx] += xl[k] * dq[n];
-      rep[a.lay.Wk + idx] += fmaf(xl[k], dk[n], Xs[k] * dkx[n]);
-      rep[a.lay.Wv + idx] += fmaf(xl[k], dv[n], Xs[k] * dvx[n]);
+    if (regacc) {
+      const float dqn = dq[rn], dkn = dk[rn], dvn = dv[rn], dkxn = dkx[rn], dvxn = dvx[rn];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const int k = rk0 + i * rkstep;
+        if (k < D) {
+          const float xlk = xl[k], xsk = Xs[k];
+          aq[i] = fmaf(xlk, dqn, aq[i]);
+          ak[i] = fmaf(xlk, dkn, fmaf(xsk, dkxn, ak[i]));
+          av[i] = fmaf(xlk, dvn, fmaf(xsk, dvxn, av[i]));
+        }
+      }
+    } else {
+      for (int idx = tid; idx < D * D; idx += 128) {
+        const int k = idx / D, n = idx - k * D;
+        rep[a.lay.Wq + idx] += xl[k] * dq[n];
+        rep[a.lay.Wk + idx] += fmaf(xl[k], dk[n], Xs[k] * dkx[n]);
+        rep[a.lay.Wv + idx] += fmaf(xl[k], dv[n], Xs[k] * dvx[n]);
+      }
     }
     // input encoding: X = (x W_in + b_in) * sqrt(D)  |  X = emb[tok] * sqrt(D)
     if (a.input_mode == SMCT_INPUT_LINEAR) {
@@ -900,6 +1065,20 @@ __global__ void __launch_bounds__(128) bwd_rows_kernel(const BwdArgs a) {
     } else if (a.input_mode == SMCT_INPUT_EMBEDDING) {
       const int tok = clamp_index(((const int*)a.x_in)[row], a.Fx);
       for (int d = tid; d < D; d += 128) rep[a.lay.W_in + (long long)tok * D + d] += dX[d] * a.sqrtD;
+    }
+  }
+  if (tid < D) {
+    rep[a.lay.ln1_g + tid] += g_ln1g; rep[a.lay.ln1_b + tid] += g_ln1b;
+    rep[a.lay.bq + tid] += g_bq; rep[a.lay.bk + tid] += g_bk; rep[a.lay.bv + tid] += g_bv;
+  }
+  if (regacc) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const int k = rk0 + i * rkstep;
+      if (k < D) {
+        const int idx = k * D + rn;
+        rep[a.lay.Wq + idx] += aq[i]; rep[a.lay.Wk + idx] += ak[i]; rep[a.lay.Wv + idx] += av[i];
+      }
     }
   }
 }

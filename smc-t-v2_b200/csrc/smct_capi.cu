@@ -530,10 +530,10 @@ size_t backward_ws(const smct_shape& s) {
   const smct::GradLayout l = make_layout(s);
   size_t n = 0;
   n += 5 * align_up(BSD * 4);                                   // X, xln, q_, kx, vx
-  n += align_up((size_t)s.D * s.D * 4) + 2 * align_up((size_t)s.D * s.dff * 4);   // transposed weights
+  n += 4 * align_up((size_t)s.D * s.D * 4) + 2 * align_up((size_t)s.D * s.dff * 4);   // transposed weights (Wz, Wq, Wk, Wv; W1, W2)
   n += align_up(BPS * 2);                                       // anc
   n += 2 * align_up(((size_t)s.B * s.S + 1) * 4);               // node_cnt, node_off
-  n += 2 * align_up(BPS * 4) + 2 * align_up(BPS * 2);           // node_bs, node_m, node_p, node_L
+  n += 2 * align_up(BPS * 4) + 3 * align_up(BPS * 2);           // node_bs, node_m, node_p, node_L, node_of
   n += 3 * align_up(BPS * s.D * 4) + align_up(BPS * 2 * 4);     // Zm, dZm, Qm, stat
   n += 6 * align_up(BSD * 4);                                   // per-row sums
   n += align_up((size_t)BWD_NREP * l.total * 4) + align_up((size_t)l.total * 4);
@@ -558,8 +558,8 @@ int launch_backward_t(const smct::BwdArgs& a, cudaStream_t st) {
   smct::bwd_dense_kernel<KD><<<(int)std::min<long long>(ntiles, a.nrep), smct::NT, smem_d, st>>>(a);
   SMCT_LAUNCH_CHECK("bwd_dense_kernel");
   if (D % 4 == 0 && D <= 64) {   // rows as one float4 per lane of a half-warp: two target slots per warp at a time
-    smct::bwd_attn_bwd_half_kernel<1><<<a.B * smct::BWD_G, smct::BWD_ANT, 0, st>>>(a);   // (<2>, d_model 128, spills at 128 registers)
-    SMCT_LAUNCH_CHECK("bwd_attn_bwd_half_kernel");
+    smct::bwd_attn_bwd_chain_kernel<<<a.B * smct::BWD_CG, smct::BWD_CNT, 0, st>>>(a);   // nodes walked by representative particle
+    SMCT_LAUNCH_CHECK("bwd_attn_bwd_chain_kernel");
   } else {
     smct::bwd_attn_bwd_kernel<KD><<<a.B * smct::BWD_G, smct::BWD_ANT, 0, st>>>(a);
     SMCT_LAUNCH_CHECK("bwd_attn_bwd_kernel");
@@ -858,6 +858,7 @@ int smct_backward(const smct_shape* shape, const smct_params* params, const smct
   float* X = c.take<float>(BSD); float* xln = c.take<float>(BSD); float* q_ = c.take<float>(BSD);
   float* kx = c.take<float>(BSD); float* vx = c.take<float>(BSD);
   float* WzT = c.take<float>((size_t)D * D); float* W1T = c.take<float>((size_t)D * s.dff); float* W2T = c.take<float>((size_t)D * s.dff);
+  float* WqT = c.take<float>((size_t)D * D); float* WkT = c.take<float>((size_t)D * D); float* WvT = c.take<float>((size_t)D * D);
   unsigned short* anc = c.take<unsigned short>(BPS);
   int* node_cnt = c.take<int>((size_t)B * S + 1);
   int* node_off = c.take<int>((size_t)B * S + 1);
@@ -865,6 +866,7 @@ int smct_backward(const smct_shape* shape, const smct_params* params, const smct
   float* node_m = c.take<float>(BPS);
   unsigned short* node_p = c.take<unsigned short>(BPS);
   unsigned short* node_L = c.take<unsigned short>(BPS);
+  unsigned short* node_of = c.take<unsigned short>(BPS);
   float* Zm = c.take<float>(BPS * D); float* dZm = c.take<float>(BPS * D); float* Qm = c.take<float>(BPS * D); float* stat = c.take<float>(BPS * 2);
   float* sums = c.take<float>(6 * BSD);   // contiguous: one memset
   float* rep = c.take<float>((size_t)BWD_NREP * lay.total);
@@ -891,6 +893,10 @@ int smct_backward(const smct_shape* shape, const smct_params* params, const smct
   SMCT_LAUNCH_CHECK("transpose_kernel");
   smct::transpose_kernel<<<64, 256, 0, st>>>(params->W2, W2T, s.dff, D);
   SMCT_LAUNCH_CHECK("transpose_kernel");
+  smct::transpose_kernel<<<64, 256, 0, st>>>(params->Wq, WqT, D, D);
+  smct::transpose_kernel<<<64, 256, 0, st>>>(params->Wk, WkT, D, D);
+  smct::transpose_kernel<<<64, 256, 0, st>>>(params->Wv, WvT, D, D);
+  SMCT_LAUNCH_CHECK("transpose_kernel");
   smct::anc_trace_kernel<<<(int)std::min<long long>(((long long)B * P + 255) / 256, 148 * 8), 256, 0, st>>>(
       B, P, S, s.len_resampling, io->i_out, anc);
   SMCT_LAUNCH_CHECK("anc_trace_kernel");
@@ -905,7 +911,8 @@ int smct_backward(const smct_shape* shape, const smct_params* params, const smct
     SMCT_LAUNCH_CHECK("node_count_kernel");
     smct::node_scan_kernel<<<1, 1024, 0, st>>>(B * S, node_cnt, node_off);
     SMCT_LAUNCH_CHECK("node_scan_kernel");
-    smct::node_fill_kernel<<<B * S, 256, smem_n, st>>>(P, anc, node_off, node_bs, node_p, node_L, node_m);
+    SMCT_CUDA(cudaMemsetAsync(node_of, 0xFF, BPS * sizeof(unsigned short), st));
+    smct::node_fill_kernel<<<B * S, 256, smem_n, st>>>(P, S, anc, node_off, node_bs, node_p, node_L, node_m, node_of);
     SMCT_LAUNCH_CHECK("node_fill_kernel");
   }
 
@@ -916,8 +923,8 @@ int smct_backward(const smct_shape* shape, const smct_params* params, const smct
   a.ln_eps = s.ln_eps; a.sigma_obs = s.sigma_obs; a.inv_n = inv_n; a.sqrtD = sqrtf((float)D);
   a.b_global0 = s.b_global0; a.seed = io->seed;
   a.x_in = io->x_in; a.X = X; a.xln = xln; a.q_ = q_; a.kx = kx; a.vx = vx;
-  a.y = io->y; a.eps = io->eps; a.classic_w = io->classic_w; a.p = *params; a.WzT = WzT; a.W1T = W1T; a.W2T = W2T;
-  a.K = io->K; a.V = io->V; a.i_out = io->i_out; a.anc = anc; a.node_off = node_off; a.node_bs = node_bs; a.node_p = node_p; a.node_L = node_L; a.node_m = node_m; a.Zm = Zm; a.dZm = dZm; a.Qm = Qm; a.stat = stat;
+  a.y = io->y; a.eps = io->eps; a.classic_w = io->classic_w; a.p = *params; a.WzT = WzT; a.W1T = W1T; a.W2T = W2T; a.WqT = WqT; a.WkT = WkT; a.WvT = WvT;
+  a.K = io->K; a.V = io->V; a.i_out = io->i_out; a.anc = anc; a.node_off = node_off; a.node_bs = node_bs; a.node_p = node_p; a.node_L = node_L; a.node_m = node_m; a.node_of = node_of; a.Zm = Zm; a.dZm = dZm; a.Qm = Qm; a.stat = stat;
   a.dq_sum = dq_sum; a.dk_sum = dk_sum; a.dv_sum = dv_sum; a.dxln_sum = dxln_sum; a.dkx_sum = dkx_sum; a.dvx_sum = dvx_sum;
   a.rep = rep; a.nrep = BWD_NREP; a.lay = lay;
   int rc;
