@@ -692,152 +692,15 @@ __global__ void __launch_bounds__(BWD_ANT) bwd_attn_bwd_kernel(const BwdArgs a) 
   }
 }
 
-// ------------------------------------------------------------------------------------------
-// attention backward, half-warp form (d_model a multiple of 4, <= 128): a row of d_model floats is held by 16 lanes
-// (128-bit loads, K4 = ceil(D/64) float4 per lane), so one warp works on TWO target slots at a time and every reduction
-// is 4 shuffle steps for two (node, slot) pairs instead of 5 for one.  Same work split as bwd_attn_bwd_kernel: BWD_G CTAs
-// per sequence share its nodes; the half-warp (w, h) owns the target slots 2w + h, + 32, + 64, ... of a pass and keeps
-// their dk / dv sums in registers.  The warp-sum form above cost 2 x (5 shuffles + 5 adds) of ~45 instructions per pair.
-// ------------------------------------------------------------------------------------------
-constexpr int BWD_TJ2 = 4;      // target slots per half-warp and pass (16 warps x 2 halves x 4 = 128 slots per pass)
-
-template <int K4>
-__global__ void __launch_bounds__(BWD_ANT) bwd_attn_bwd_half_kernel(const BwdArgs a) {
-  const int D = a.D, S = a.S;
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int l16 = lane & 15, hsel = lane >> 4;
-  constexpr int NWA = BWD_ANT / 32;
-  const int b = blockIdx.x / BWD_G, g = blockIdx.x % BWD_G;
-  const float inv_sqrt_d = 1.0f / sqrtf((float)D);
-  bool okd[K4];
-  float4 c_k[K4], c_v[K4];   // 1/sigma^2 (per dimension when logvar_dim = D) times the loss normalisation
-#pragma unroll
-  for (int k = 0; k < K4; ++k) {
-    const int d = 4 * l16 + 64 * k;
-    okd[k] = d < D;
-    float ck[4], cv[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int li = (a.logvar_dim > 1 && okd[k]) ? d + e : 0;
-      ck[e] = expf(-a.p.logvar_k[li]) * a.inv_n; cv[e] = expf(-a.p.logvar_v[li]) * a.inv_n;
-    }
-    c_k[k] = make_float4(ck[0], ck[1], ck[2], ck[3]); c_v[k] = make_float4(cv[0], cv[1], cv[2], cv[3]);
-  }
-  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  auto ld4g = [&](const float* p, int k) { return okd[k] ? *reinterpret_cast<const float4*>(p + 4 * l16 + 64 * k) : zero4; };
-  auto dot4 = [](const float4& x, const float4& y, float acc) { return fmaf(x.x, y.x, fmaf(x.y, y.y, fmaf(x.z, y.z, fmaf(x.w, y.w, acc)))); };
-  auto axpy4 = [](float s_, const float4& x, float4& y) { y.x = fmaf(s_, x.x, y.x); y.y = fmaf(s_, x.y, y.y); y.z = fmaf(s_, x.z, y.z); y.w = fmaf(s_, x.w, y.w); };
-  const long long u_begin = a.node_off[(long long)b * S], u_end = a.node_off[(long long)(b + 1) * S];
-  for (int tbase = 0; tbase < S; tbase += 2 * NWA * BWD_TJ2) {
-    float4 dk[BWD_TJ2][K4], dv[BWD_TJ2][K4];
-#pragma unroll
-    for (int j = 0; j < BWD_TJ2; ++j)
-#pragma unroll
-      for (int k = 0; k < K4; ++k) { dk[j][k] = zero4; dv[j][k] = zero4; }
-    const int t0 = tbase + 2 * wid + hsel;               // this half-warp's first target slot of the pass
-    for (long long u = u_begin + g; u < u_end; u += BWD_G) {
-      const int bs = a.node_bs[u];
-      const int s = bs % S;
-      if (s < tbase + 2 * wid) continue;                   // no target slot of this warp is visible to the node (warp-uniform)
-      const int s_lo = (a.attn_window >= 0 && s > a.attn_window) ? s - a.attn_window : 0;
-      const long long bp = (long long)b * a.P + a.node_p[u];
-      const float* Kp = a.K + bp * S * D;
-      const float* Vp = a.V + bp * S * D;
-      float4 q[K4], dz[K4], dq[K4];
-      float part0 = 0.f;
-#pragma unroll
-      for (int k = 0; k < K4; ++k) {
-        q[k] = ld4g(a.Qm + u * D, k);
-        dz[k] = ld4g(a.dZm + u * D, k);
-        part0 = dot4(dz[k], ld4g(a.Zm + u * D, k), part0);
-        dq[k] = zero4;
-      }
-      const float delta = half_sum(part0);     // sum_tau a_tau (dz . v_tau) = dz . z_   (both halves hold the same node)
-      const float m = a.stat[u * 2], l = a.stat[u * 2 + 1];
-#pragma unroll
-      for (int j = 0; j < BWD_TJ2; ++j) {
-        const int t = t0 + 2 * NWA * j;
-        const bool valid = (t <= s) && (t >= s_lo);        // uniform per half-warp; the shuffles below are executed by all lanes
-        float4 kr[K4], vr[K4];
-        float pk = 0.f, pv = 0.f;
-#pragma unroll
-        for (int k = 0; k < K4; ++k) {
-          kr[k] = valid ? ld4g(Kp + (long long)t * D, k) : zero4;
-          vr[k] = valid ? ld4g(Vp + (long long)t * D, k) : zero4;
-          pk = dot4(q[k], kr[k], pk);
-          pv = dot4(dz[k], vr[k], pv);
-        }
-        const float sc = half_sum(pk) * inv_sqrt_d;
-        const float dA = half_sum(pv);
-        if (valid) {
-          const float at = expf(sc - m) / l;
-          const float dS = at * (dA - delta) * inv_sqrt_d;
-#pragma unroll
-          for (int k = 0; k < K4; ++k) {
-            axpy4(dS, kr[k], dq[k]);
-            axpy4(dS, q[k], dk[j][k]);
-            axpy4(at, dz[k], dv[j][k]);
-          }
-          if (t == s) {
-            // direct terms of the loss on the resampled K/V noises of the node's own row: 1/2 ||K - kx||^2 / sigma_k^2
-            // (same for V), once per final particle that descends from the node
-            const float mult = a.node_m[u];
-#pragma unroll
-            for (int k = 0; k < K4; ++k) {
-              if (okd[k]) {
-                const int d = 4 * l16 + 64 * k;
-                const float4 kx = *reinterpret_cast<const float4*>(a.kx + (long long)bs * D + d);
-                const float4 vx = *reinterpret_cast<const float4*>(a.vx + (long long)bs * D + d);
-                const float tk[4] = {mult * c_k[k].x * (kr[k].x - kx.x), mult * c_k[k].y * (kr[k].y - kx.y),
-                                     mult * c_k[k].z * (kr[k].z - kx.z), mult * c_k[k].w * (kr[k].w - kx.w)};
-                const float tv[4] = {mult * c_v[k].x * (vr[k].x - vx.x), mult * c_v[k].y * (vr[k].y - vx.y),
-                                     mult * c_v[k].z * (vr[k].z - vx.z), mult * c_v[k].w * (vr[k].w - vx.w)};
-                dk[j][k].x += tk[0]; dk[j][k].y += tk[1]; dk[j][k].z += tk[2]; dk[j][k].w += tk[3];
-                dv[j][k].x += tv[0]; dv[j][k].y += tv[1]; dv[j][k].z += tv[2]; dv[j][k].w += tv[3];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  atomicAdd(a.dkx_sum + (long long)bs * D + d + e, -tk[e]);
-                  atomicAdd(a.dvx_sum + (long long)bs * D + d + e, -tv[e]);
-                }
-              }
-            }
-          }
-        }
-      }
-      // dq of the node: the two halves worked on different slots; combine, then one native global RED per element
-#pragma unroll
-      for (int k = 0; k < K4; ++k) {
-        dq[k].x += __shfl_xor_sync(SMCT_FULL_MASK, dq[k].x, 16); dq[k].y += __shfl_xor_sync(SMCT_FULL_MASK, dq[k].y, 16);
-        dq[k].z += __shfl_xor_sync(SMCT_FULL_MASK, dq[k].z, 16); dq[k].w += __shfl_xor_sync(SMCT_FULL_MASK, dq[k].w, 16);
-        if (hsel == 0 && okd[k]) {
-          float* dst = a.dq_sum + (long long)bs * D + 4 * l16 + 64 * k;
-          atomicAdd(dst, dq[k].x); atomicAdd(dst + 1, dq[k].y); atomicAdd(dst + 2, dq[k].z); atomicAdd(dst + 3, dq[k].w);
-        }
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < BWD_TJ2; ++j) {
-      const int t = t0 + 2 * NWA * j;
-      if (t < S) {
-#pragma unroll
-        for (int k = 0; k < K4; ++k) {
-          if (okd[k]) {
-            float* dkp = a.dk_sum + ((long long)b * S + t) * D + 4 * l16 + 64 * k;
-            float* dvp = a.dv_sum + ((long long)b * S + t) * D + 4 * l16 + 64 * k;
-            atomicAdd(dkp, dk[j][k].x); atomicAdd(dkp + 1, dk[j][k].y); atomicAdd(dkp + 2, dk[j][k].z); atomicAdd(dkp + 3, dk[j][k].w);
-            atomicAdd(dvp, dv[j][k].x); atomicAdd(dvp + 1, dv[j][k].y); atomicAdd(dvp + 2, dv[j][k].z); atomicAdd(dvp + 3, dv[j][k].w);
-          }
-        }
-      }
-    }
-  }
-}
+constexpr int BWD_TJ2 = 4;      // target slots per half-warp and pass
 
 // ------------------------------------------------------------------------------------------
-// attention backward over CHAINS (d_model a multiple of 4, <= 64): the same arithmetic and work split as the half-warp
-// form below, but the nodes are walked by representative particle.  All nodes represented by particle p lie on p's
+// attention backward over CHAINS (d_model a multiple of 4, <= 64).  A row of d_model floats is held by 16 lanes (128-bit
+// loads), so one warp works on TWO target slots at a time and every reduction is 4 shuffle steps for two (node, slot)
+// pairs; BWD_CG CTAs per sequence share its nodes; the half-warp (w, h) owns the target slots 2w + h, + 2 NWA, ... of a pass
+// and keeps their dk / dv sums in registers.  The nodes are walked by representative particle.  All nodes represented by particle p lie on p's
 // lineage, so they attend over the SAME rows K[b,p,0..s], V[b,p,0..s]: a half-warp loads the rows of its target slots
-// once per chain and keeps them in registers for every node of the chain.  The half-warp form reloaded 512 B per
+// once per chain and keeps them in registers for every node of the chain.  The previous form (nodes in list order) reloaded 512 B per
 // (node, slot) pair (27 GB of DRAM reads per 296 C4 sequences, 59 % of its stall samples on those loads, 17.7 ms);
 // here the K / V tensors are read once.
 // ------------------------------------------------------------------------------------------
