@@ -325,6 +325,29 @@ __global__ void __launch_bounds__(256) bwd_attn_fwd_half_kernel(const BwdArgs a)
 // its PT products in row order; the blocked path (2 k x 4 n per thread: 6 shared loads per 8 FMAs instead of 2 per 1)
 // gives the same bits as the scalar one.
 __device__ __forceinline__ void tile_outer_accum(const float* A, int lda, const float* Bm, int ldb, int Kdim, int N, float* rep) {
+  if ((Kdim & 1) == 0 && (N & 3) == 0 && (lda & 1) == 0 && (ldb & 3) == 0 && (reinterpret_cast<uintptr_t>(A) & 7) == 0 &&
+      (reinterpret_cast<uintptr_t>(Bm) & 15) == 0) {
+    // vector loads (rows padded to a multiple of 4 floats): one 64-bit + one 128-bit shared load per 8 FMAs; same sums
+    const int N4 = N >> 2, K2 = Kdim >> 1;
+    for (int idx = threadIdx.x; idx < K2 * N4; idx += NT) {
+      const int k = 2 * (idx / N4), n = 4 * (idx % N4);
+      float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+#pragma unroll 4
+      for (int r = 0; r < PT; ++r) {
+        const float2 a01 = *reinterpret_cast<const float2*>(A + r * lda + k);
+        const float4 b = *reinterpret_cast<const float4*>(Bm + r * ldb + n);
+        acc[0][0] = fmaf(a01.x, b.x, acc[0][0]); acc[0][1] = fmaf(a01.x, b.y, acc[0][1]);
+        acc[0][2] = fmaf(a01.x, b.z, acc[0][2]); acc[0][3] = fmaf(a01.x, b.w, acc[0][3]);
+        acc[1][0] = fmaf(a01.y, b.x, acc[1][0]); acc[1][1] = fmaf(a01.y, b.y, acc[1][1]);
+        acc[1][2] = fmaf(a01.y, b.z, acc[1][2]); acc[1][3] = fmaf(a01.y, b.w, acc[1][3]);
+      }
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) rep[(k + i) * N + n + e] += acc[i][e];
+    }
+    return;
+  }
   if ((Kdim & 1) == 0 && (N & 3) == 0) {
     const int N4 = N >> 2, K2 = Kdim >> 1;
     for (int idx = threadIdx.x; idx < K2 * N4; idx += NT) {
@@ -358,7 +381,8 @@ __device__ __forceinline__ void tile_outer_accum(const float* A, int lda, const 
 template <int KD>
 __global__ void __launch_bounds__(NT) bwd_dense_kernel(const BwdArgs a) {
   extern __shared__ float sm[];
-  const int D = a.D, Dp = D + 1, dff = a.dff, Fp = dff + 1, S = a.S, Fy = a.Fy;
+  // row strides: a multiple of 4 floats when the width is (vector loads in the tile GEMMs), else width + 1
+  const int D = a.D, Dp = (a.D & 3) ? a.D + 1 : a.D + 4, dff = a.dff, Fp = (a.dff & 3) ? a.dff + 1 : a.dff + 4, S = a.S, Fy = a.Fy;
   float* Zt = sm;                 // z_ tile
   float* Ut = Zt + PT * Dp;       // normalised LN1 input (u hat)
   float* Ot = Ut + PT * Dp;       // o = LN1(z + x)

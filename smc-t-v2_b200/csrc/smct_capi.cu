@@ -548,7 +548,7 @@ int launch_backward_t(const smct::BwdArgs& a, cudaStream_t st) {
   if (D % 4 == 0 && D <= 64) smct::bwd_attn_fwd_half_kernel<<<(int)std::min<long long>((nrows + 7) / 8, 148LL * 64), 256, 0, st>>>(a);
   else smct::bwd_attn_fwd_kernel<KD><<<(int)std::min<long long>((nrows + 7) / 8, 148LL * 64), 256, 0, st>>>(a);
   SMCT_LAUNCH_CHECK("bwd_attn_fwd_kernel");
-  const size_t smem_d = ((size_t)5 * smct::PT * (D + 1) + 2 * smct::PT * (dff + 1) + smct::PT + 7 * D + dff + D * a.Fy) * sizeof(float);
+  const size_t smem_d = ((size_t)5 * smct::PT * (D + 4) + 2 * smct::PT * (dff + 4) + smct::PT + 7 * D + dff + D * a.Fy) * sizeof(float);   // (strides: smct_backward.cuh)
   if (smem_d > 200 * 1024) return fail(SMCT_ERR_UNSUPPORTED, "backward dense tile needs %zu B shared memory", smem_d);
   static PerDeviceOnce attr_once;
   if (attr_once.need()) {
