@@ -179,6 +179,14 @@ __global__ void transpose_kernel(const float* in, float* out, int rows, int cols
   }
 }
 
+// 2^x on the special-function unit (the half-warp attention kernels keep scores and softmax maxima in the log2 domain,
+// like the fused forward: one MUFU instead of the ~8-instruction expf)
+__device__ __forceinline__ float bwd_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 __device__ __forceinline__ float half_sum(float v) {   // sum over the 16 lanes of a half-warp (all 32 lanes participate)
 #pragma unroll
   for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(SMCT_FULL_MASK, v, o);
@@ -262,7 +270,7 @@ __global__ void __launch_bounds__(256) bwd_attn_fwd_half_kernel(const BwdArgs a)
   float std_q[4];
 #pragma unroll
   for (int e = 0; e < 4; ++e) std_q[e] = expf(0.5f * a.p.logvar_q[(multi && okd) ? d0 + e : 0]);
-  const float inv_sqrt_d = 1.0f / sqrtf((float)D);
+  const float qk_scale = 1.4426950408889634f / sqrtf((float)D);   // scores in the log2 domain (stat[] holds the log2-domain maximum)
   const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
   for (long long u = (long long)blockIdx.x * 8 + wid; u < nnodes; u += (long long)gridDim.x * 8) {
     const int bs = a.node_bs[u];
@@ -287,10 +295,10 @@ __global__ void __launch_bounds__(256) bwd_attn_fwd_half_kernel(const BwdArgs a)
       const bool valid = t <= s;                      // uniform per half-warp; all lanes execute the shuffles
       const float4 kv = (valid && okd) ? *reinterpret_cast<const float4*>(Kp + (long long)t * D + d0) : zero4;
       const float4 vr = (valid && okd) ? *reinterpret_cast<const float4*>(Vp + (long long)t * D + d0) : zero4;
-      const float sc = half_sum(fmaf(q.x, kv.x, fmaf(q.y, kv.y, fmaf(q.z, kv.z, q.w * kv.w)))) * inv_sqrt_d;
+      const float sc = half_sum(fmaf(q.x, kv.x, fmaf(q.y, kv.y, fmaf(q.z, kv.z, q.w * kv.w)))) * qk_scale;
       if (valid) {
         const float mn = fmaxf(m, sc);
-        const float corr = expf(m - mn), pj = expf(sc - mn);
+        const float corr = bwd_ex2(m - mn), pj = bwd_ex2(sc - mn);
         l = l * corr + pj;
         acc.x = fmaf(pj, vr.x, acc.x * corr); acc.y = fmaf(pj, vr.y, acc.y * corr);
         acc.z = fmaf(pj, vr.z, acc.z * corr); acc.w = fmaf(pj, vr.w, acc.w * corr);
@@ -302,7 +310,7 @@ __global__ void __launch_bounds__(256) bwd_attn_fwd_half_kernel(const BwdArgs a)
     const float4 ao = make_float4(__shfl_xor_sync(SMCT_FULL_MASK, acc.x, 16), __shfl_xor_sync(SMCT_FULL_MASK, acc.y, 16),
                                   __shfl_xor_sync(SMCT_FULL_MASK, acc.z, 16), __shfl_xor_sync(SMCT_FULL_MASK, acc.w, 16));
     const float mt = fmaxf(m, mo);
-    const float ca = expf(m - mt), cb = (mo == -INFINITY) ? 0.f : expf(mo - mt);
+    const float ca = bwd_ex2(m - mt), cb = (mo == -INFINITY) ? 0.f : bwd_ex2(mo - mt);
     // both halves form the same totals in the same order (lower half's terms first)
     const float l_lo = hsel ? lo : l, l_hi = hsel ? l : lo, c_lo = hsel ? cb : ca, c_hi = hsel ? ca : cb;
     const float lt = l_lo * c_lo + l_hi * c_hi;
@@ -738,6 +746,7 @@ __global__ void __launch_bounds__(BWD_CNT, 2) bwd_attn_bwd_chain_kernel(const Bw
   constexpr int NWA = BWD_CNT / 32;
   const int b = blockIdx.x / BWD_CG, g = blockIdx.x % BWD_CG;
   const float inv_sqrt_d = 1.0f / sqrtf((float)D);
+  const float qk_scale = 1.4426950408889634f * inv_sqrt_d;   // log2-domain scores, like bwd_attn_fwd_half_kernel's stat[]
   const int d0 = 4 * l16;
   const bool okd = d0 < D;
   float ck[4], cv[4];   // 1/sigma^2 (per dimension when logvar_dim = D) times the loss normalisation
@@ -800,10 +809,10 @@ __global__ void __launch_bounds__(BWD_CNT, 2) bwd_attn_bwd_chain_kernel(const Bw
           for (int j = 0; j < BWD_TJ2; ++j) {
             const int t = t0 + 2 * NWA * j;
             const bool valid = (t <= s) && (t >= s_lo);    // uniform per half-warp; the shuffles are executed by all lanes
-            const float sc = half_sum(dot4(q, kr[j])) * inv_sqrt_d;
+            const float sc = half_sum(dot4(q, kr[j])) * qk_scale;
             const float dA = half_sum(dot4(dz, vr[j]));
             if (valid) {
-              const float at = expf(sc - m) * inv_l;
+              const float at = bwd_ex2(sc - m) * inv_l;
               const float dS = at * (dA - delta) * inv_sqrt_d;
               axpy4(dS, kr[j], dq);
               axpy4(dS, q, dk[j]);
