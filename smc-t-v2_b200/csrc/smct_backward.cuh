@@ -290,6 +290,7 @@ __global__ void __launch_bounds__(256) bwd_attn_fwd_half_kernel(const BwdArgs a)
     const float* Vp = a.V + bp * S * D;
     float m = -INFINITY, l = 0.f;
     float4 acc = zero4;
+#pragma unroll 4   // four rows' loads in flight per half-warp (the loop is bound by the latency of its K / V row loads)
     for (int tb = s_lo; tb <= s; tb += 2) {
       const int t = tb + hsel;
       const bool valid = t <= s;                      // uniform per half-warp; all lanes execute the shuffles
