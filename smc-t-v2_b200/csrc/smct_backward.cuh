@@ -336,6 +336,32 @@ __global__ void __launch_bounds__(256) bwd_attn_fwd_half_kernel(const BwdArgs a)
 __device__ __forceinline__ void tile_outer_accum(const float* A, int lda, const float* Bm, int ldb, int Kdim, int N, float* rep) {
   if ((Kdim & 1) == 0 && (N & 3) == 0 && (lda & 1) == 0 && (ldb & 3) == 0 && (reinterpret_cast<uintptr_t>(A) & 7) == 0 &&
       (reinterpret_cast<uintptr_t>(Bm) & 15) == 0) {
+    if ((Kdim & 3) == 0 && (lda & 3) == 0 && (reinterpret_cast<uintptr_t>(A) & 15) == 0) {
+      // 4 k x 4 n per thread: two 128-bit shared loads per 16 FMAs; same sums (row order)
+      const int N4q = N >> 2, K4q = Kdim >> 2;
+      for (int idx = threadIdx.x; idx < K4q * N4q; idx += NT) {
+        const int k = 4 * (idx / N4q), n = 4 * (idx % N4q);
+        float acc[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+#pragma unroll 4
+        for (int r = 0; r < PT; ++r) {
+          const float4 a4 = *reinterpret_cast<const float4*>(A + r * lda + k);
+          const float4 b = *reinterpret_cast<const float4*>(Bm + r * ldb + n);
+          const float av[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            acc[i][0] = fmaf(av[i], b.x, acc[i][0]); acc[i][1] = fmaf(av[i], b.y, acc[i][1]);
+            acc[i][2] = fmaf(av[i], b.z, acc[i][2]); acc[i][3] = fmaf(av[i], b.w, acc[i][3]);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) rep[(k + i) * N + n + e] += acc[i][e];
+      }
+      return;
+    }
     // vector loads (rows padded to a multiple of 4 floats): one 64-bit + one 128-bit shared load per 8 FMAs; same sums
     const int N4 = N >> 2, K2 = Kdim >> 1;
     for (int idx = threadIdx.x; idx < K2 * N4; idx += NT) {

@@ -133,6 +133,40 @@ __device__ __forceinline__ void tile_gemm(const float* __restrict__ A, int lda, 
     // sums its products in k order: identical bits.
     constexpr int RH = PT / 2;
     const int N4 = N >> 2, K4 = Kdim >> 2;
+    if (N4 * (PT / 4) >= (int)blockDim.x) {
+      // wide outputs (every thread still has work with 4 rows x 4 columns): 8 loads per 64 FMAs
+      constexpr int RQ = PT / 4;   // rows rg, rg + RQ, rg + 2 RQ, rg + 3 RQ
+      for (int j = threadIdx.x; j < N4 * RQ; j += (int)blockDim.x) {
+        const int c = 4 * (j % N4), rg = j / N4;
+        float acc[4][4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { const float b0 = bias ? bias[c + e] : 0.f; acc[0][e] = acc[1][e] = acc[2][e] = acc[3][e] = b0; }
+        const float* Wc = W + c;
+#pragma unroll 2
+        for (int k4 = 0; k4 < K4; ++k4) {
+          float av[4][4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 t = *reinterpret_cast<const float4*>(A + (rg + i * RQ) * lda + 4 * k4);
+            av[i][0] = t.x; av[i][1] = t.y; av[i][2] = t.z; av[i][3] = t.w;
+          }
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            const float4 w = __ldg(reinterpret_cast<const float4*>(Wc + (long long)(4 * k4 + kk) * N));
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              acc[i][0] = fmaf(av[i][kk], w.x, acc[i][0]); acc[i][1] = fmaf(av[i][kk], w.y, acc[i][1]);
+              acc[i][2] = fmaf(av[i][kk], w.z, acc[i][2]); acc[i][3] = fmaf(av[i][kk], w.w, acc[i][3]);
+            }
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) epi(rg + i * RQ, c + e, acc[i][e]);
+      }
+      return;
+    }
     for (int j = threadIdx.x; j < N4 * RH; j += (int)blockDim.x) {
       const int c = 4 * (j % N4), rg = j / N4;
       float acc[2][4];
